@@ -1,0 +1,157 @@
+// flof_api.cu -- context, device memory pool and copies of the C ABI (include/flof_b200.h).
+//
+// ref: FluidSolver owns a stack-like pool of grid buffers (fluidsolver.cpp:24-53, 94-126).
+// B200-native equivalent: one CUDA stream per context and the device's stream-ordered memory
+// pool with an unlimited release threshold, so Grid4d temporaries are recycled without
+// cudaMalloc/cudaFree round trips; 180 GB of HBM3e hold every grid of a 128^4 solve resident.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "flof_common.cuh"
+
+static char g_create_err[512] = "";
+
+int flof_fail(flof_ctx *ctx, int code, const char *fmt, ...)
+{
+	char *buf = ctx ? ctx->err : g_create_err;
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, 512, fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+extern "C" {
+
+int flof_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+int flof_ctx_create(flof_ctx **out, int device)
+{
+	flof_ctx *ctx = NULL;
+	if (!out) return flof_fail(NULL, FLOF_ERR_ARG, "flof_ctx_create: out is NULL");
+	*out = NULL;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0)
+		return flof_fail(NULL, FLOF_ERR_CUDA,
+		                 "flof_ctx_create: no CUDA device (%s); libflof_b200 has no CPU fallback",
+		                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	if (device < 0 || device >= n)
+		return flof_fail(NULL, FLOF_ERR_ARG, "flof_ctx_create: device %d out of range (0..%d)",
+		                 device, n - 1);
+	flof_ctx *c = (flof_ctx *)calloc(1, sizeof(flof_ctx));
+	if (!c) return flof_fail(NULL, FLOF_ERR_NOMEM, "flof_ctx_create: out of host memory");
+	c->device = device;
+#define CCK(call)                                                                             \
+	do {                                                                                      \
+		cudaError_t e__ = (call);                                                             \
+		if (e__ != cudaSuccess) {                                                             \
+			flof_fail(NULL, FLOF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));  \
+			free(c);                                                                          \
+			return FLOF_ERR_CUDA;                                                             \
+		}                                                                                     \
+	} while (0)
+	CCK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CCK(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) {
+		flof_fail(NULL, FLOF_ERR_CUDA,
+		          "flof_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+		          device, prop.major, prop.minor);
+		free(c);
+		return FLOF_ERR_CUDA;
+	}
+	c->sm_count = prop.multiProcessorCount;
+	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CCK(cudaDeviceGetDefaultMemPool(&c->pool, device));
+	uint64_t thr = UINT64_MAX;
+	CCK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+	CCK(cudaMalloc((void **)&c->red, sizeof(flof_reduce_scratch)));
+	CCK(cudaMemset(c->red, 0, sizeof(flof_reduce_scratch)));
+	CCK(cudaMalloc((void **)&c->cg, sizeof(flof_cg_state)));
+	CCK(cudaMemset(c->cg, 0, sizeof(flof_cg_state)));
+	CCK(cudaMallocHost(&c->pinned, 4096));
+	for (int i = 0; i < 4; ++i) CCK(cudaEventCreate(&c->ev[i]));
+#undef CCK
+	(void)ctx;
+	*out = c;
+	return FLOF_OK;
+}
+
+int flof_ctx_destroy(flof_ctx *ctx)
+{
+	if (!ctx) return FLOF_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
+	cudaFreeHost(ctx->pinned);
+	cudaFree(ctx->cg);
+	cudaFree(ctx->red);
+	cudaStreamDestroy(ctx->stream);
+	free(ctx);
+	return FLOF_OK;
+}
+
+const char *flof_last_error(flof_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+void *flof_ctx_stream(flof_ctx *ctx) { return (void *)ctx->stream; }
+long long flof_ctx_launch_count(flof_ctx *ctx) { return ctx->launches; }
+
+int flof_malloc(flof_ctx *ctx, void **dptr, size_t bytes)
+{
+	FLOF_ARG(dptr != NULL, "flof_malloc: dptr is NULL");
+	return flof_tmp_alloc(ctx, dptr, bytes, true);
+}
+int flof_free(flof_ctx *ctx, void *dptr) { return flof_tmp_free(ctx, dptr); }
+
+int flof_memcpy_h2d(flof_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+	FLOF_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	return FLOF_OK;
+}
+int flof_memcpy_d2h(flof_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+	FLOF_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	FLOF_CK(cudaStreamSynchronize(ctx->stream));
+	return FLOF_OK;
+}
+int flof_memcpy_d2d(flof_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+	FLOF_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	return FLOF_OK;
+}
+int flof_memset0(flof_ctx *ctx, void *dst, size_t bytes)
+{
+	FLOF_CK(cudaMemsetAsync(dst, 0, bytes, ctx->stream));
+	return FLOF_OK;
+}
+int flof_sync(flof_ctx *ctx)
+{
+	FLOF_CK(cudaStreamSynchronize(ctx->stream));
+	return FLOF_OK;
+}
+
+} /* extern "C" */
+
+int flof_tmp_alloc(flof_ctx *ctx, void **p, size_t bytes, bool zero)
+{
+	if (bytes == 0) bytes = 16;
+	cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+	if (e != cudaSuccess) {
+		*p = NULL;
+		return flof_fail(ctx, e == cudaErrorMemoryAllocation ? FLOF_ERR_NOMEM : FLOF_ERR_CUDA,
+		                 "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+	}
+	if (zero) FLOF_CK(cudaMemsetAsync(*p, 0, bytes, ctx->stream));
+	return FLOF_OK;
+}
+int flof_tmp_free(flof_ctx *ctx, void *p)
+{
+	if (!p) return FLOF_OK;
+	FLOF_CK(cudaFreeAsync(p, ctx->stream));
+	return FLOF_OK;
+}

@@ -1,0 +1,178 @@
+// flof_blur.cu -- truncated 4D Gaussian blur, 81-tap extrapolation blur, border reset.
+// ref: gaussianWeight / knGaussianBlur / gaussianBlurGeneric optflow4d.cpp:128-174,
+//      knCvExpolBlur4d :613-626 (driver loop :770-780), border reset :544-551.
+//
+// Parity mode: the Gaussian is evaluated exactly like the reference -- the full (2s+1)^4 box,
+// taps visited in the order vt, zk, yj, xi, each `val += w*a` an fp32 multiply then add, the
+// weight sum accumulated in the same order over the in-bounds taps only -- so the result is
+// bit-identical to the CPU.  That makes this kernel FP32-issue bound rather than HBM bound
+// (625 taps x 9 instructions per cell for s = 2); the data it touches per pass is still just
+// 16 B in + 16 B out per cell and stays L1/L2 resident across the taps.
+#include <math.h>
+
+#include "flof_common.cuh"
+
+#define FLOF_BLUR_MAXS 4
+// weight by integer squared distance, ref gaussianWeight :128-131: exp(-dSqr/(2.*sigma*sigma))
+__constant__ float c_gauss_w[4 * FLOF_BLUR_MAXS * FLOF_BLUR_MAXS + 1];
+
+template <class T> __device__ __forceinline__ T blur_zero();
+template <> __device__ __forceinline__ float blur_zero<float>() { return 0.f; }
+template <> __device__ __forceinline__ float4 blur_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void blur_acc(float &v, float w, float a) { v += w * a; }
+__device__ __forceinline__ void blur_acc(float4 &v, float w, const float4 &a)
+{
+	v.x += w * a.x; v.y += w * a.y; v.z += w * a.z; v.w += w * a.w;
+}
+__device__ __forceinline__ float blur_div(float v, float w) { return v / w; }
+__device__ __forceinline__ float4 blur_div(const float4 &v, float w)
+{
+	return make_float4(v.x / w, v.y / w, v.z / w, v.w / w);
+}
+
+// one thread per interior cell (bnd 1); dst cells on the border shell are left untouched,
+// which reproduces the zero border of the fresh tmp grid after pass 1 and the original border
+// after pass 2 (ref :160-174) because the caller ping-pongs the same two buffers.
+template <class T, int S>
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_gauss_blur4d(const T *__restrict__ a, T *__restrict__ tmp, flof_dim4 d)
+{
+	int i, j, k, t;
+	if (!flof_cell_ijkt(d, i, j, k, t)) return;
+	if (!flof_in_bounds(d, i, j, k, t, 1)) return;
+	T val = blur_zero<T>();
+	float weight = 0.f;
+	const int x0 = max(i - S, 0), x1 = min(i + S, d.nx - 1);
+	for (int vt = t - S; vt <= t + S; ++vt) {
+		if (vt < 0 || vt >= d.nt) continue;
+		const int dt2 = (vt - t) * (vt - t);
+		for (int zk = k - S; zk <= k + S; ++zk) {
+			if (zk < 0 || zk >= d.nz) continue;
+			const int dz2 = dt2 + (zk - k) * (zk - k);
+			for (int yj = j - S; yj <= j + S; ++yj) {
+				if (yj < 0 || yj >= d.ny) continue;
+				const int dy2 = dz2 + (yj - j) * (yj - j);
+				const T *row = a + flof_idx(d, 0, yj, zk, vt);
+				for (int xi = x0; xi <= x1; ++xi) {
+					const float wcurr = c_gauss_w[dy2 + (xi - i) * (xi - i)];
+					weight += wcurr;
+					blur_acc(val, wcurr, __ldg(row + xi));
+				}
+			}
+		}
+	}
+	const int64_t c = flof_idx(d, i, j, k, t);
+	if (weight > FLOF_VECTOR_EPSILON)
+		tmp[c] = blur_div(val, weight);
+	else
+		tmp[c] = __ldg(a + c);
+}
+
+template <class T>
+static int launch_blur(flof_ctx *ctx, const T *a, T *tmp, flof_dim4 d, int s)
+{
+	switch (s) {
+	case 1: FLOF_LAUNCH((k_gauss_blur4d<T, 1>), flof_grid4(d), FLOF_BLOCK, 0, a, tmp, d); break;
+	case 2: FLOF_LAUNCH((k_gauss_blur4d<T, 2>), flof_grid4(d), FLOF_BLOCK, 0, a, tmp, d); break;
+	case 3: FLOF_LAUNCH((k_gauss_blur4d<T, 3>), flof_grid4(d), FLOF_BLOCK, 0, a, tmp, d); break;
+	case 4: FLOF_LAUNCH((k_gauss_blur4d<T, 4>), flof_grid4(d), FLOF_BLOCK, 0, a, tmp, d); break;
+	default: return flof_fail(ctx, FLOF_ERR_ARG, "gaussianBlur: kernel half-width %d > %d unsupported", s, FLOF_BLUR_MAXS);
+	}
+	return FLOF_OK;
+}
+
+int flof_gaussian_blur4d_impl(flof_ctx *ctx, float *a, flof_dim4 d, int elem, float sigma, int iter)
+{
+	FLOF_ARG(elem == 1 || elem == 4, "gaussianBlur: elem must be 1 or 4");
+	int s = (int)(1. * sigma + 0.5);  // ref :165
+	if (s == 0) s = 1;
+	FLOF_ARG(s <= FLOF_BLUR_MAXS, "gaussianBlur: sigma %g too large (half-width %d > %d)", sigma, s, FLOF_BLUR_MAXS);
+	float w[4 * FLOF_BLUR_MAXS * FLOF_BLUR_MAXS + 1];
+	for (int q = 0; q <= 4 * s * s; ++q) {
+		const float dSqr = (float)q;
+		w[q] = (float)exp(-dSqr / (2. * sigma * sigma));
+	}
+	FLOF_CK(cudaMemcpyToSymbolAsync(c_gauss_w, w, sizeof(float) * (4 * s * s + 1), 0, cudaMemcpyHostToDevice,
+	                                ctx->stream));
+	const size_t bytes = sizeof(float) * (size_t)elem * (size_t)flof_cells(d);
+	void *tmp = NULL;
+	FLOF_RET(flof_tmp_alloc(ctx, &tmp, bytes, true));  // GRID tmp(parent): zero-initialised
+	float *cur = a, *oth = (float *)tmp;
+	int rc = FLOF_OK;
+	for (int numIt = 0; numIt < 2 * iter && rc == FLOF_OK; ++numIt) {
+		if (elem == 4)
+			rc = launch_blur<float4>(ctx, (const float4 *)cur, (float4 *)oth, d, s);
+		else
+			rc = launch_blur<float>(ctx, cur, oth, d, s);
+		float *sw = cur; cur = oth; oth = sw;  // a.swap(tmp)
+	}
+	// 2*iter swaps: `cur` is the caller's buffer again
+	flof_tmp_free(ctx, tmp);
+	return rc;
+}
+
+extern "C" int flof_gaussian_blur4d(flof_ctx *ctx, float *a, flof_dim4 d, int elem, float sigma, int iter)
+{
+	return flof_gaussian_blur4d_impl(ctx, a, d, elem, sigma, iter);
+}
+
+// ------------------------------------------------------------------ 81-tap extrapolation ---
+// ref knCvExpolBlur4d :613-626: where marker == 0 (interior, bnd 1) tmp = (sum of the 3^4
+// neighbourhood in vt,zk,yj,xi order) * (1./81.); elsewhere tmp keeps the copy of a.
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_cv_expol_blur4d(const float4 *__restrict__ a, float4 *__restrict__ tmp, const float *__restrict__ mark,
+                      flof_dim4 d)
+{
+	int i, j, k, t;
+	if (!flof_cell_ijkt(d, i, j, k, t)) return;
+	const int64_t c = flof_idx(d, i, j, k, t);
+	if (!flof_in_bounds(d, i, j, k, t, 1) || __ldg(mark + c) != 0.f) {
+		tmp[c] = __ldg(a + c);  // tmp.copyFrom(dst) fused in
+		return;
+	}
+	float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+	for (int vt = t - 1; vt <= t + 1; ++vt)
+		for (int zk = k - 1; zk <= k + 1; ++zk)
+			for (int yj = j - 1; yj <= j + 1; ++yj) {
+				const float4 *row = a + flof_idx(d, i - 1, yj, zk, vt);
+#pragma unroll
+				for (int xi = 0; xi < 3; ++xi) {
+					const float4 q = __ldg(row + xi);
+					val.x += q.x; val.y += q.y; val.z += q.z; val.w += q.w;
+				}
+			}
+	const double f = 1. / 81.0;  // Vec4 * double, rounded per component
+	tmp[c] = make_float4((float)(val.x * f), (float)(val.y * f), (float)(val.z * f), (float)(val.w * f));
+}
+
+extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker, flof_dim4 d, int sweeps)
+{
+	if (sweeps <= 0) return FLOF_OK;
+	const size_t bytes = sizeof(float) * 4 * (size_t)flof_cells(d);
+	void *tmp = NULL;
+	FLOF_RET(flof_tmp_alloc(ctx, &tmp, bytes, false));
+	float *cur = a, *oth = (float *)tmp;
+	for (int sIt = 0; sIt < sweeps; ++sIt) {
+		FLOF_LAUNCH(k_cv_expol_blur4d, flof_grid4(d), FLOF_BLOCK, 0, (const float4 *)cur, (float4 *)oth, marker, d);
+		float *sw = cur; cur = oth; oth = sw;
+	}
+	int rc = FLOF_OK;
+	if (cur != a) rc = flof_memcpy_d2d(ctx, a, cur, bytes);
+	flof_tmp_free(ctx, tmp);
+	return rc;
+}
+
+// ------------------------------------------------------------------ border reset -----------
+// ref :544-551: everything outside isInBounds(resetBnd) -> 0
+__global__ void k_reset_border_vec4(float4 *__restrict__ vel, flof_dim4 d, int resetBnd)
+{
+	int i, j, k, t;
+	if (!flof_cell_ijkt(d, i, j, k, t)) return;
+	if (flof_in_bounds(d, i, j, k, t, resetBnd)) return;
+	vel[flof_idx(d, i, j, k, t)] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+int flof_reset_border_vec4(flof_ctx *ctx, float *vel, flof_dim4 d, int resetBnd)
+{
+	FLOF_LAUNCH(k_reset_border_vec4, flof_grid4(d), FLOF_BLOCK, 0, (float4 *)vel, d, resetBnd);
+	return FLOF_OK;
+}

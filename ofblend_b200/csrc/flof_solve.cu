@@ -1,0 +1,481 @@
+// flof_solve.cu -- 4D optical-flow system assembly and the matrix-free Jacobi-PCG.
+// ref: FixedMatrixOF / applyMat / dotProd / getMaxNorm / addScaled / GridCGOptflow4d
+//      optflow4d.cpp:179-355 and opticalFlowDim<.,.,4> :361-553.
+//
+// Design (B200): the reference stores the matrix explicitly (offd N + blockd 4N floats, 17 GB at
+// 128^4).  Here the system is matrix-free: per cell only grad (float4) and rhs (float4) are kept;
+// the 4x4 block  grad grad^T + diag*I  and the Jacobi preconditioner are recomputed in registers
+// with the reference's fp32 operation order, so every matrix entry has the identical fp32 value.
+// Unknown layout = Vec4 AoS (idx = cell*4 + d, ref :60-64), i.e. one 128-bit access per cell.
+//
+// One CG iteration = three flat kernels over the cells (224 B/cell/iteration):
+//   A: tmp = A*srch                       (+ partial fp64 dot(srch,tmp))
+//   B: result += alpha*srch; res -= alpha*tmp   (+ partial signed max(res), fp64 dot(res*precond,res))
+//   C: srch = res*precond + beta*srch     (stop test first)
+// Scalars (alpha, beta, sigma, residual) never leave the device: each reducing kernel ends with a
+// "last block finishes" pass that sums the per-block partials in index order (deterministic) and
+// updates the flof_cg_state; the host only polls the `done` flag every few iterations.
+// Border rows are identity with zero rhs (ref :424-433): marked by grad.x = NaN so the solver
+// kernels need no index arithmetic at all.
+#include <math.h>
+
+#include "flof_common.cuh"
+
+int flof_reset_border_vec4(flof_ctx *ctx, float *vel, flof_dim4 d, int resetBnd);
+int flof_optical_flow4d_ex(flof_ctx *ctx, float *vel, const float *i0, const float *i1, float *rhsT, flof_dim4 d,
+                           float wSmooth, float wEnergy, float postVelBlur, float cgAccuracy,
+                           float resetBndWidth, int vel_is_zero, int *cgIters, float *cgRes);
+
+struct flof_of_consts {
+	float offd;   // -wSmooth * mDx2Inv          ref :476
+	float diag;   // 8*wSmooth*mDx2Inv + wEnergy ref :478-480
+};
+
+static flof_of_consts of_consts(float wSmooth, float wEnergy)
+{
+	flof_of_consts k;
+	const float mDx2Inv = 1.f;
+	k.offd = -wSmooth * mDx2Inv;
+	volatile float diag = 0.f;
+	diag += (float)(2 * 4) * wSmooth * mDx2Inv;
+	diag += wEnergy;
+	k.diag = diag;
+	return k;
+}
+
+// ------------------------------------------------------------------ K1 assembly -----------
+// ref :398-493.  Reads i0, i1 (+ the 6/8 stencil neighbours of i1 from cache) and, only if
+// has_vel, the incoming vel with its clamped neighbours; writes grad and rhs (16 B each).
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_of_assemble(float4 *__restrict__ grad, float4 *__restrict__ rhs, const float *__restrict__ i0,
+                  const float *__restrict__ i1, const float4 *__restrict__ vel, flof_dim4 d,
+                  float wSmooth, float wEnergy, float mDx, float dxf, int has_vel)
+{
+	int i, j, k, t;
+	if (!flof_cell_ijkt(d, i, j, k, t)) return;
+	const int64_t c = flof_idx(d, i, j, k, t);
+	if (!flof_in_bounds(d, i, j, k, t, 1)) {
+		grad[c] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);  // identity-row marker
+		rhs[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+		return;
+	}
+	const int64_t sY = d.nx, sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
+	const float mDt = 1.0f;
+	const float tderiv = (__ldg(i1 + c) - __ldg(i0 + c)) / mDt;
+	float g[4];
+	g[0] = (__ldg(i1 + c + 1) - __ldg(i1 + c - 1)) * dxf;
+	g[1] = (__ldg(i1 + c + sY) - __ldg(i1 + c - sY)) * dxf;
+	g[2] = (__ldg(i1 + c + sZ) - __ldg(i1 + c - sZ)) * dxf;
+	g[3] = (__ldg(i1 + c + sT) - __ldg(i1 + c - sT)) * dxf;
+	float r[4];
+#pragma unroll
+	for (int dd = 0; dd < 4; ++dd) r[dd] = -g[dd] * tderiv;
+	if (has_vel) {
+		// smoothness + Tikhonov terms of the incoming field (ref :463-472, 491); neighbour
+		// order t-1, z-1, y-1, x-1, x+1, y+1, z+1, t+1 with clamped indices
+		const float4 vc4 = __ldg(vel + c);
+		const float vc[4] = { vc4.x, vc4.y, vc4.z, vc4.w };
+		const int nb[8][4] = { { 0, 0, 0, -1 }, { 0, 0, -1, 0 }, { 0, -1, 0, 0 }, { -1, 0, 0, 0 },
+			                   { 1, 0, 0, 0 },  { 0, 1, 0, 0 },  { 0, 0, 1, 0 },  { 0, 0, 0, 1 } };
+		float4 vn4[8];
+#pragma unroll
+		for (int m = 0; m < 8; ++m) {
+			const int ti = max(0, min(d.nx - 1, i + nb[m][0])), tj = max(0, min(d.ny - 1, j + nb[m][1]));
+			const int tk = max(0, min(d.nz - 1, k + nb[m][2])), tt = max(0, min(d.nt - 1, t + nb[m][3]));
+			vn4[m] = __ldg(vel + flof_idx(d, ti, tj, tk, tt));
+		}
+#pragma unroll
+		for (int dd = 0; dd < 4; ++dd) {
+#pragma unroll
+			for (int m = 0; m < 8; ++m) {
+				const float vn = dd == 0 ? vn4[m].x : (dd == 1 ? vn4[m].y : (dd == 2 ? vn4[m].z : vn4[m].w));
+				r[dd] -= wSmooth * (vc[dd] - vn) * mDx * 1.f;
+			}
+			r[dd] -= wEnergy * vc[dd] * mDx;
+		}
+	}
+	grad[c] = make_float4(g[0], g[1], g[2], g[3]);
+	rhs[c] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+extern "C" int flof_of_assemble(flof_ctx *ctx, float *grad, float *rhs, const float *i0,
+                                const float *i1, const float *vel, flof_dim4 d, float wSmooth,
+                                float wEnergy)
+{
+	FLOF_ARG(d.nx >= 3 && d.ny >= 3 && d.nz >= 3 && d.nt >= 3, "opticalFlow4d: grid too small");
+	const float mDx = (float)(1. / d.nx);           // ref :369
+	const float dxf = (float)(1. / (2. * mDx));     // ref :441
+	FLOF_LAUNCH(k_of_assemble, flof_grid4(d), FLOF_BLOCK, 0, (float4 *)grad, (float4 *)rhs, i0, i1,
+	            (const float4 *)vel, d, wSmooth, wEnergy, mDx, dxf, vel != NULL);
+	return FLOF_OK;
+}
+
+// ------------------------------------------------------------------ CG kernels ------------
+__device__ __forceinline__ bool is_border(const float4 &g) { return g.x != g.x; }
+
+// reciprocal Jacobi diagonal, ref precondInit :331-343: precond = 1./diag, diag = blockd(i,i)
+__device__ __forceinline__ float4 precond_of(const float4 &g, float diag)
+{
+	if (is_border(g)) return make_float4(1.f, 1.f, 1.f, 1.f);
+	return make_float4(1.0f / (g.x * g.x + diag), 1.0f / (g.y * g.y + diag), 1.0f / (g.z * g.z + diag),
+	                   1.0f / (g.w * g.w + diag));
+}
+__device__ __forceinline__ double dot4(const float4 &a, const float4 &b)
+{  // ref dotProd :234-241: fp32 products accumulated in double
+	double s = (double)(a.x * b.x);
+	s += (double)(a.y * b.y);
+	s += (double)(a.z * b.z);
+	s += (double)(a.w * b.w);
+	return s;
+}
+__device__ __forceinline__ float axpy1(float a, double b, float c)
+{  // ref addScaled :253-258: a = float(double(a) + b*double(c))
+	return (float)((double)a + b * (double)c);
+}
+
+// res = rhs, result = 0, tmp = res*precond, srch = tmp; residual0 = max(res), sigma = tmp.res
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_cg_init(float4 *__restrict__ x, float4 *__restrict__ res, float4 *__restrict__ srch,
+              const float4 *__restrict__ grad, const float4 *__restrict__ rhs, int64_t cells, float diag,
+              float accuracy, flof_reduce_scratch *red, flof_cg_state *st)
+{
+	__shared__ double shd[32];
+	__shared__ float shf[32];
+	double dsum = 0.;
+	float mx = -3.402823466e+38f;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
+		const float4 g = __ldg(grad + c), r = __ldg(rhs + c);
+		const float4 pc = precond_of(g, diag);
+		const float4 z = make_float4(r.x * pc.x, r.y * pc.y, r.z * pc.z, r.w * pc.w);
+		x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+		res[c] = r;
+		srch[c] = z;
+		dsum += dot4(z, r);
+		mx = fmaxf(mx, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
+	}
+	dsum = flof_block_sum(dsum, shd);
+	mx = flof_block_max(mx, shf);
+	if (threadIdx.x == 0) {
+		red->dsum[0][blockIdx.x] = dsum;
+		red->fmax[blockIdx.x] = mx;
+	}
+	if (flof_last_block(&red->counter[1])) {
+		double s = 0.;
+		float m = -3.402823466e+38f;
+		for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+			s += red->dsum[0][b];
+			m = fmaxf(m, red->fmax[b]);
+		}
+		s = flof_block_sum(s, shd);
+		m = flof_block_max(m, shf);
+		if (threadIdx.x == 0) {
+			const double residual = (double)m;  // ref :286
+			st->iter = 0;
+			st->done = 0;
+			st->status = 0;
+			st->residual = m;
+			st->relResidual = 1e10f;  // cgRes initial value, ref :499
+			st->resIni = residual;
+			st->acc = (double)accuracy * residual;  // ref :292
+			st->sigma[0] = s;
+			st->sigma[1] = s;
+			st->alpha1 = 0.;
+			st->sigmaNew = 0.;
+			if (residual < (double)FLOF_VECTOR_EPSILON) {  // ref :287-291
+				st->done = 1;
+				st->status = 2;
+				st->relResidual = 0.f;
+			} else if (s == 0. || s != s) {  // ref :298-301
+				st->done = 1;
+				st->status = 3;
+			}
+		}
+	}
+}
+
+// A: tmp = A * srch (ref applyMat :211-232), partial dot(srch, tmp)
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_cg_apply(float4 *__restrict__ tmp, const float4 *__restrict__ srch, const float4 *__restrict__ grad,
+               int64_t cells, int64_t sY, int64_t sZ, int64_t sT, float offd, float diag,
+               flof_reduce_scratch *red, flof_cg_state *st)
+{
+	if (st->done) return;
+	__shared__ double shd[32];
+	double dsum = 0.;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
+		const float4 g = __ldg(grad + c);
+		const float4 p = __ldg(srch + c);
+		float4 v;
+		if (is_border(g)) {
+			v = p;  // identity row
+		} else {
+			v = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (offd != 0.f) {
+				// neighbour order of nbx/nby/nbz/nbt (ref :389-392): t-1, z-1, y-1, x-1, x+1, y+1, z+1, t+1
+				const int64_t o[8] = { -sT, -sZ, -sY, -1, 1, sY, sZ, sT };
+#pragma unroll
+				for (int m = 0; m < 8; ++m) {
+					const float4 q = __ldg(srch + c + o[m]);
+					v.x += offd * q.x; v.y += offd * q.y; v.z += offd * q.z; v.w += offd * q.w;
+				}
+			}
+			// block row d: sum_m blockd(d,m) * x_m, blockd(d,m) = g_d*g_m (+ diag if d == m)  ref :483-488
+			const float gg[4] = { g.x, g.y, g.z, g.w };
+			const float pp[4] = { p.x, p.y, p.z, p.w };
+			float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+			for (int dd = 0; dd < 4; ++dd) {
+#pragma unroll
+				for (int m = 0; m < 4; ++m) {
+					const float b = (dd == m) ? (gg[dd] * gg[m] + diag) : (gg[dd] * gg[m]);
+					vv[dd] += b * pp[m];
+				}
+			}
+			v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+		}
+		tmp[c] = v;
+		dsum += dot4(p, v);
+	}
+	dsum = flof_block_sum(dsum, shd);
+	if (threadIdx.x == 0) red->dsum[0][blockIdx.x] = dsum;
+	if (flof_last_block(&red->counter[1])) {
+		double s = 0.;
+		for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += red->dsum[0][b];
+		s = flof_block_sum(s, shd);
+		if (threadIdx.x == 0) st->alpha1 = s;
+	}
+}
+
+// B: alpha = sigma/alpha1; result += alpha*srch; res -= alpha*tmp; partial max(res), dot(res*precond, res)
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_cg_update(float4 *__restrict__ x, float4 *__restrict__ res, const float4 *__restrict__ srch,
+                const float4 *__restrict__ tmp, const float4 *__restrict__ grad, int64_t cells, float diag,
+                flof_reduce_scratch *red, flof_cg_state *st)
+{
+	if (st->done) return;
+	__shared__ double shd[32];
+	__shared__ float shf[32];
+	const double sigma = st->sigma[st->iter & 1];
+	const double alpha = sigma / st->alpha1;  // ref :307-308
+	const double nalpha = -alpha;
+	double dsum = 0.;
+	float mx = -3.402823466e+38f;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
+		const float4 p = __ldg(srch + c), ap = __ldg(tmp + c), g = __ldg(grad + c);
+		float4 xv = x[c], r = res[c];
+		xv.x = axpy1(xv.x, alpha, p.x); xv.y = axpy1(xv.y, alpha, p.y);
+		xv.z = axpy1(xv.z, alpha, p.z); xv.w = axpy1(xv.w, alpha, p.w);
+		r.x = axpy1(r.x, nalpha, ap.x); r.y = axpy1(r.y, nalpha, ap.y);
+		r.z = axpy1(r.z, nalpha, ap.z); r.w = axpy1(r.w, nalpha, ap.w);
+		x[c] = xv;
+		res[c] = r;
+		const float4 pc = precond_of(g, diag);
+		const float4 z = make_float4(r.x * pc.x, r.y * pc.y, r.z * pc.z, r.w * pc.w);
+		dsum += dot4(z, r);
+		mx = fmaxf(mx, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
+	}
+	dsum = flof_block_sum(dsum, shd);
+	mx = flof_block_max(mx, shf);
+	if (threadIdx.x == 0) {
+		red->dsum[1][blockIdx.x] = dsum;
+		red->fmax[blockIdx.x] = mx;
+	}
+	if (flof_last_block(&red->counter[2])) {
+		double s = 0.;
+		float m = -3.402823466e+38f;
+		for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+			s += red->dsum[1][b];
+			m = fmaxf(m, red->fmax[b]);
+		}
+		s = flof_block_sum(s, shd);
+		m = flof_block_max(m, shf);
+		if (threadIdx.x == 0) {
+			st->sigmaNew = s;
+			st->residual = m;
+			st->relResidual = (float)((double)m / st->resIni);  // ref :312
+		}
+	}
+}
+
+// C: stop test (ref :314-317), else srch = res*precond + beta*srch (ref :318-323)
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_cg_direction(float4 *__restrict__ srch, const float4 *__restrict__ res, const float4 *__restrict__ grad,
+                   int64_t cells, float diag, int maxIter, flof_cg_state *st)
+{
+	if (st->done) return;
+	const int it = st->iter;
+	const double sigma = st->sigma[it & 1], sigmaNew = st->sigmaNew;
+	const bool converged = ((double)st->residual <= st->acc);
+	if (!converged) {
+		const double beta = sigmaNew / sigma;
+		const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+		for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
+			const float4 r = __ldg(res + c), g = __ldg(grad + c);
+			const float4 pc = precond_of(g, diag);
+			float4 p = srch[c];
+			p.x = axpy1(r.x * pc.x, beta, p.x); p.y = axpy1(r.y * pc.y, beta, p.y);
+			p.z = axpy1(r.z * pc.z, beta, p.z); p.w = axpy1(r.w * pc.w, beta, p.w);
+			srch[c] = p;
+		}
+	}
+}
+
+// single-thread epilogue of an iteration: advance the device-side CG state (runs after C)
+__global__ void k_cg_advance(int maxIter, flof_cg_state *st)
+{
+	if (st->done) return;
+	const int it = st->iter;
+	st->iter = it + 1;  // ret_iterations = iter + 1
+	if ((double)st->residual <= st->acc) {
+		st->done = 1;
+		st->status = 1;
+		return;
+	}
+	st->sigma[(it + 1) & 1] = st->sigmaNew;
+	if (it + 1 >= maxIter) st->done = 1;  // ref: loop bound cgMaxIter, returns false
+}
+
+// ref :520-529 copy back: vel = result / mDx, optional rhsT = rhs[d=0]
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_of_copy_back(float4 *__restrict__ vel, const float4 *__restrict__ x, const float4 *__restrict__ rhs,
+                   float *__restrict__ rhsT, int64_t cells, float mDx)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
+		const float4 v = __ldg(x + c);
+		vel[c] = make_float4(v.x / mDx, v.y / mDx, v.z / mDx, v.w / mDx);
+		if (rhsT) rhsT[c] = __ldg(rhs + c).x;
+	}
+}
+
+static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, const float *grad,
+                  const float *rhs, flof_dim4 d, float wSmooth, float wEnergy, float accuracy,
+                  int maxIter, int *iters, float *relRes, int *status)
+{
+	const int64_t cells = flof_cells(d);
+	const flof_of_consts k = of_consts(wSmooth, wEnergy);
+	const int blocks = flof_flat_blocks(ctx, cells, 8);
+	const int64_t sY = d.nx, sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
+	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, (float4 *)x, (float4 *)res, (float4 *)srch,
+	            (const float4 *)grad, (const float4 *)rhs, cells, k.diag, accuracy, ctx->red, ctx->cg);
+	flof_cg_state *h = (flof_cg_state *)ctx->pinned;
+	int launched = 0;
+	// poll the device-side done flag every `chunk` iterations; iterations after convergence are
+	// no-op kernels (early return on st->done)
+	int chunk = 8;
+	while (true) {
+		FLOF_CK(cudaMemcpyAsync(h, ctx->cg, sizeof(flof_cg_state), cudaMemcpyDeviceToHost, ctx->stream));
+		FLOF_CK(cudaStreamSynchronize(ctx->stream));
+		if (h->done || launched >= maxIter) break;
+		for (int q = 0; q < chunk && launched < maxIter; ++q, ++launched) {
+			FLOF_LAUNCH(k_cg_apply, blocks, FLOF_BLOCK, 0, (float4 *)tmp, (const float4 *)srch,
+			            (const float4 *)grad, cells, sY, sZ, sT, k.offd, k.diag, ctx->red, ctx->cg);
+			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, (float4 *)x, (float4 *)res, (const float4 *)srch,
+			            (const float4 *)tmp, (const float4 *)grad, cells, k.diag, ctx->red, ctx->cg);
+			FLOF_LAUNCH(k_cg_direction, blocks, FLOF_BLOCK, 0, (float4 *)srch, (const float4 *)res,
+			            (const float4 *)grad, cells, k.diag, maxIter, ctx->cg);
+			FLOF_LAUNCH(k_cg_advance, 1, 1, 0, maxIter, ctx->cg);
+		}
+		if (launched >= 32) chunk = 16;
+	}
+	*iters = h->iter;
+	*relRes = h->relResidual;
+	*status = h->status;
+	return FLOF_OK;
+}
+
+extern "C" int flof_of_cg(flof_ctx *ctx, float *x, const float *grad, const float *rhs, flof_dim4 d,
+                          float wSmooth, float wEnergy, float accuracy, int maxIter, int *iters,
+                          float *relResidual)
+{
+	const size_t vb = sizeof(float) * 4 * (size_t)flof_cells(d);
+	void *res = NULL, *srch = NULL, *tmp = NULL;
+	FLOF_RET(flof_tmp_alloc(ctx, &res, vb, false));
+	FLOF_RET(flof_tmp_alloc(ctx, &srch, vb, false));
+	FLOF_RET(flof_tmp_alloc(ctx, &tmp, vb, false));
+	int st = 0, it = 0;
+	float rr = 0.f;
+	int rc = cg_run(ctx, x, (float *)res, (float *)srch, (float *)tmp, grad, rhs, d, wSmooth, wEnergy,
+	                accuracy, maxIter, &it, &rr, &st);
+	flof_tmp_free(ctx, res);
+	flof_tmp_free(ctx, srch);
+	flof_tmp_free(ctx, tmp);
+	if (iters) *iters = it;
+	if (relResidual) *relResidual = rr;
+	return rc;
+}
+
+int flof_gaussian_blur4d_impl(flof_ctx *ctx, float *a, flof_dim4 d, int elem, float sigma, int iter);
+
+// ctx-level timing hooks for the multi-scale trace (device time of the CG part of the last call)
+float g_flof_last_cg_ms = 0.f;
+
+extern "C" int flof_optical_flow4d(flof_ctx *ctx, float *vel, const float *i0, const float *i1,
+                                   float *rhsT, flof_dim4 d, float wSmooth, float wEnergy,
+                                   float postVelBlur, float cgAccuracy, float resetBndWidth,
+                                   int *cgIters, float *cgRes)
+{
+	return flof_optical_flow4d_ex(ctx, vel, i0, i1, rhsT, d, wSmooth, wEnergy, postVelBlur, cgAccuracy,
+	                              resetBndWidth, 0, cgIters, cgRes);
+}
+
+// vel_is_zero: the caller guarantees the incoming field is all zero (the multi-step driver solves
+// for a fresh zero field every time, ref :1046, 1119).  Then every smoothness / Tikhonov rhs term
+// is +-0 and `rhs -= 0` is the identity, so the assembly skips reading vel -- bit-identical.
+int flof_optical_flow4d_ex(flof_ctx *ctx, float *vel, const float *i0, const float *i1, float *rhsT, flof_dim4 d,
+                           float wSmooth, float wEnergy, float postVelBlur, float cgAccuracy,
+                           float resetBndWidth, int vel_is_zero, int *cgIters, float *cgRes)
+{
+	FLOF_ARG(d.nx >= 3 && d.ny >= 3 && d.nz >= 3 && d.nt >= 3, "opticalFlow4d: grid too small");
+	const int64_t cells = flof_cells(d);
+	FLOF_ARG(cells < ((int64_t)1 << 29), "opticalFlow4d: N = cells*4 exceeds int range (ref :376)");
+	const size_t vb = sizeof(float) * 4 * (size_t)cells;
+	void *grad = NULL, *rhs = NULL, *x = NULL, *res = NULL, *srch = NULL, *tmp = NULL;
+	FLOF_RET(flof_tmp_alloc(ctx, &grad, vb, false));
+	FLOF_RET(flof_tmp_alloc(ctx, &rhs, vb, false));
+	FLOF_RET(flof_tmp_alloc(ctx, &x, vb, false));
+	FLOF_RET(flof_tmp_alloc(ctx, &res, vb, false));
+	FLOF_RET(flof_tmp_alloc(ctx, &srch, vb, false));
+	FLOF_RET(flof_tmp_alloc(ctx, &tmp, vb, false));
+	int rc = flof_of_assemble(ctx, (float *)grad, (float *)rhs, i0, i1, vel_is_zero ? NULL : vel, d, wSmooth, wEnergy);
+	int it = 0, st = 0;
+	float rr = 1e10f;
+	if (rc == FLOF_OK) {
+		cudaEventRecord(ctx->ev[2], ctx->stream);
+		rc = cg_run(ctx, (float *)x, (float *)res, (float *)srch, (float *)tmp, (const float *)grad,
+		            (const float *)rhs, d, wSmooth, wEnergy, cgAccuracy, 1000, &it, &rr, &st);
+		cudaEventRecord(ctx->ev[3], ctx->stream);
+	}
+	if (rc == FLOF_OK) {
+		if (rr != rr) {  // ref :509-514 NaN -> zero the solution
+			rc = flof_memset0(ctx, x, vb);
+		}
+	}
+	if (rc == FLOF_OK) {
+		const float mDx = (float)(1. / d.nx);
+		FLOF_LAUNCH(k_of_copy_back, flof_flat_blocks(ctx, cells, 8), FLOF_BLOCK, 0, (float4 *)vel,
+		            (const float4 *)x, (const float4 *)rhs, rhsT, cells, mDx);
+	}
+	flof_tmp_free(ctx, grad);
+	flof_tmp_free(ctx, rhs);
+	flof_tmp_free(ctx, x);
+	flof_tmp_free(ctx, res);
+	flof_tmp_free(ctx, srch);
+	flof_tmp_free(ctx, tmp);
+	if (rc != FLOF_OK) return rc;
+	// ref :532-541 optional blur with half sigma
+	if (postVelBlur > 0.f) FLOF_RET(flof_gaussian_blur4d_impl(ctx, vel, d, 4, (float)(0.5 * postVelBlur), 1));
+	// ref :544-551 reset outer border
+	if (resetBndWidth > 0.f) {
+		const int resetBnd = (int)(resetBndWidth * d.nx) + 1;
+		FLOF_RET(flof_reset_border_vec4(ctx, vel, d, resetBnd));
+	}
+	FLOF_CK(cudaEventSynchronize(ctx->ev[3]));
+	cudaEventElapsedTime(&g_flof_last_cg_ms, ctx->ev[2], ctx->ev[3]);
+	if (cgIters) *cgIters = it;
+	if (cgRes) *cgRes = rr;
+	return FLOF_OK;
+}
