@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- FlOF mode-1 4D deformation solve on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--res 64] [--impl ours|reference]
+
+A "step" is one full mode-1 deformation solve (opticalFlowMultiscale4d with the README solver
+parameters of scenes/flof.py:304-320, 913-915: pyramid, 3 OF steps per level, final SDF
+projection) on a synthetic two-drop 4D SDF pair (BASELINE.json configs[3]: 64^4).
+
+One JSON line:
+  value        seconds per solve, inputs resident in HBM (CUDA-event timed on the library's stream)
+  e2e          the same solve through the host-buffer plugin call flof_optical_flow_multiscale4d_host:
+               H2D of i0, i1, vel from pinned memory and D2H of the deformation inside the timed region
+  roofline     dominant kernel: algorithmic bytes per launch / its average duration, measured live with
+               CUDA events bracketing every launch (flof_profile_begin/end) in K extra steps
+  cpu_baseline the reference's own CPU implementation (oracle/_ref, else our C port) on a bounded sample
+--impl reference times that CPU implementation as the reference arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "flof_mode1_4d_deformation_solve_wall_time"
+UNIT = "s"
+
+# algorithmic bytes per cell and launch (SURVEY.md §8d / DESIGN.md §4)
+KERNEL_BYTES_PER_CELL = {
+    "k_cg_apply": 48,         # srch 16 + grad 16 -> tmp 16
+    "k_cg_update": 112,       # result, res, srch, tmp, grad 80 -> result, res 32
+    "k_cg_direction": 64,     # res, grad, srch 48 -> srch 16
+    "k_gauss_blur4d": 32,     # Vec4 in 16 -> Vec4 out 16 per pass
+    "k_cv_expol_blur4d": 36,  # a 16 + marker 4 -> tmp 16
+    "k_project_cells": 44,    # vel 16, phiOrg 4, phiTarget 4 -> dst 16, marker 4
+    "k_semi_lagrange4d<float4>": 48,
+    "k_semi_lagrange4d<float>": 24,
+    "k_of_assemble": 40,
+}
+
+
+def peaks():
+    fn = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(fn):
+        try:
+            return float(json.load(open(fn))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_solve(res, threads=None):
+    """One mode-1 solve by the reference's CPU implementation on a `res`^4 synthetic pair.
+    Returns (seconds, kind, cores, cg_iters)."""
+    from oracle import ref
+    from ofblend_b200 import synth
+    if ref.available():
+        mod, kind = ref, "reference"
+    else:
+        from oracle import port as mod
+        kind = "port"
+    cores = mod.set_threads(threads or (os.cpu_count() or 1))
+
+    class Ops:
+        set_bound4d = staticmethod(lambda a, v, w: mod.set_bound4d(a, v, w))
+        extrap4d_ls_simple = staticmethod(lambda a, d, i: mod.extrap4d_ls_simple(a, d, i))
+        mult_const = staticmethod(lambda a, s: mod.grid_op4d("multConst", a, None, s))
+
+    dims = (res, res, res, res)
+    i0 = synth.post_process(synth.two_drop_phi(dims, 0), Ops)
+    i1 = synth.post_process(synth.two_drop_phi(dims, 1), Ops)
+    v0 = np.zeros(i0.shape + (4,), np.float32)
+    t0 = time.time()
+    mod.optical_flow_multiscale4d(v0, i0, i1, **synth.MODE1_PARAMS)
+    return time.time() - t0, kind, cores
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample_res = 32 if args.res >= 64 else max(16, args.res // 2)
+    scale = (args.res / sample_res) ** 4
+    times = []
+    kind = cores = None
+    for s in range(args.warmup + args.steps):
+        if s < args.warmup and s > 0:
+            continue  # one warm-up solve is enough to page the library in; CPU timing has no clocks to settle
+        sec, kind, cores = cpu_reference_solve(sample_res)
+        if s >= args.warmup:
+            times.append(sec)
+    sec = float(np.mean(times)) * scale
+    sample = ("%s CPU implementation, full mode-1 solve on the %d^4 synthetic two-drop pair (1/%d of the cells of the "
+              "%d^4 workload), wall time scaled x%d by cell count" % (kind, sample_res, int(scale), args.res, int(scale)))
+    line = {"metric": METRIC, "value": sec, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "flof mode 1 (opticalFlowMultiscale4d, README parameters) on synthetic two-drop "
+                                   "4D SDF pair %d^4" % args.res, "res": args.res},
+            "cpu_baseline": {"value": sec, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--res", type=int, default=64)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from ofblend_b200 import capi, synth
+    ctx = capi.Context(local_rank)
+    api = capi.HostAPI(ctx)
+    res = args.res
+    dims = (res, res, res, res)
+    cells = res ** 4
+
+    # inputs: synthetic two-drop pair, pre-processed on the GPU by the product kernels (outside the timed region)
+    i0_h = synth.post_process(synth.two_drop_phi(dims, 0), api)
+    i1_h = synth.post_process(synth.two_drop_phi(dims, 1), api)
+    i0 = ctx.to_device(i0_h)
+    i1 = ctx.to_device(i1_h)
+    vel = ctx.grid(dims, 4)
+    params = capi.make_params(**synth.MODE1_PARAMS)
+    zero4 = np.zeros(4, np.float32)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def one_step():
+        ctx.grid_set_const(vel, zero4)
+        return ctx.optical_flow_multiscale4d(vel, i0, i1, params, want_trace=True)
+
+    for _ in range(args.warmup):
+        one_step()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    cg_ms = 0.0
+    cg_updates = 0
+    trace = None
+    for _ in range(args.steps):
+        err, trace = one_step()
+        dev_ms += trace.total_ms
+        n = min(trace.n_solves, 64)
+        cg_ms += sum(trace.cg_ms[:n])
+        cg_updates += sum(int(trace.cg_iters[q]) * int(trace.cg_cells[q]) for q in range(n))
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.launches - launches0
+
+    # device time (CUDA events on the library's stream, recorded inside the call); max over ranks
+    ms_per_step = dev_ms / args.steps
+    if dist is not None:
+        import torch
+        tmax = torch.tensor([ms_per_step], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_per_step = float(tmax.item())
+
+    # ---- e2e: host buffers through the plugin-level C-ABI call, copies inside the timed region
+    hb = {}
+    for name, nbytes in (("i0", cells * 4), ("i1", cells * 4), ("vel", cells * 16)):
+        p = C.c_void_p()
+        ctx._chk(ctx.lib.flof_host_alloc(ctx.h, C.byref(p), C.c_size_t(nbytes)))
+        hb[name] = (p, np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(nbytes // 4,)))
+    hb["i0"][1][:] = i0_h.ravel()
+    hb["i1"][1][:] = i1_h.ravel()
+    e2e_times = []
+    tr2 = capi.MultiscaleTrace()
+    e2 = C.c_float(0)
+    for s in range(1 + args.steps):
+        hb["vel"][1][:] = 0.0
+        barrier()
+        t1 = time.perf_counter()
+        ctx._chk(ctx.lib.flof_optical_flow_multiscale4d_host(ctx.h, hb["vel"][0], hb["i0"][0], hb["i1"][0],
+                                                             capi.Dim4(*dims), C.byref(params), C.byref(tr2), C.byref(e2)))
+        result_norm = float(hb["vel"][1][:4096].sum())  # touch the result on the host
+        barrier()
+        if s > 0:
+            e2e_times.append(time.perf_counter() - t1)
+    e2e_s = float(np.mean(e2e_times))
+    if dist is not None:
+        import torch
+        tmax = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- live per-kernel timing: CUDA events bracket every launch of K more steps of the same workload
+    # (kept out of the steps timed above so the ~2 event records per launch do not perturb `value`)
+    stats = (KernelStat * 256)()
+    nstat = C.c_int(0)
+    prof_steps = max(1, min(args.steps, 3))
+    ctx._chk(ctx.lib.flof_profile_begin(ctx.h))
+    for _ in range(prof_steps):
+        one_step()
+    ctx._chk(ctx.lib.flof_profile_end(ctx.h, stats, 256, C.byref(nstat)))
+    tot_ms = sum(stats[q].total_ms for q in range(nstat.value))
+    peak, peak_src = peaks()
+    ktab = []
+    for q in range(nstat.value):
+        nm = stats[q].name.decode().replace("(", "").replace(")", "")
+        key = next((k for k in KERNEL_BYTES_PER_CELL if nm.startswith(k)), None)
+        row = {"kernel": nm, "cells": int(stats[q].cells), "launches_per_step": stats[q].launches / prof_steps,
+               "ms_per_step": stats[q].total_ms / prof_steps, "avg_launch_ms": stats[q].total_ms / stats[q].launches,
+               "share": stats[q].total_ms / max(tot_ms, 1e-9)}
+        if key is not None and stats[q].cells > 0:
+            row["bytes_per_launch"] = KERNEL_BYTES_PER_CELL[key] * int(stats[q].cells)
+            row["gbs"] = row["bytes_per_launch"] / (row["avg_launch_ms"] * 1e-3) / 1e9
+            row["frac"] = row["gbs"] / peak
+        ktab.append(row)
+    dom = next((r for r in ktab if "gbs" in r), None)  # ktab is sorted by total time: dominant (kernel, level)
+    if dom is not None:
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "cells_per_launch": dom["cells"], "achieved": dom["gbs"],
+                    "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": dom["bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
+                    "share_of_step": dom["share"],
+                    "how": "CUDA events around every launch on the library stream, %d steps" % prof_steps}
+    else:
+        roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
+
+    line = {"metric": METRIC, "value": ms_per_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
+            "scaling": "strong" if world == 1 else "replicas", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "flof mode 1 (opticalFlowMultiscale4d, README parameters: wSmooth 1e-3, wEnergy 1e-4, "
+                                   "cgAccuracy 1e-2, postVelBlur 4, multiStep 3, minGridSize 20, final projection) on "
+                                   "synthetic two-drop 4D SDF pair %d^4" % res,
+                       "res": res, "levels": [res >> l for l in range(8) if (res >> l) > 10 and (l == 0 or (res >> (l - 1)) > 20)],
+                       "l2": "working set (%d MB of grids) exceeds the 126 MB L2; no explicit flush" % (cells * 4 * 30 // 2 ** 20),
+                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (t-sharding: next round)" % world},
+            "wall_ms_per_step": wall / args.steps * 1e3,
+            "cg_cell_updates_per_s": cg_updates / max(cg_ms * 1e-3, 1e-12),
+            "cg_iters": [int(trace.cg_iters[q]) for q in range(min(trace.n_solves, 64))],
+            "final_error": float(trace.errs[min(trace.n_errs, 64) - 1]) if trace.n_errs else None,
+            "gpu_launches": int(launches),
+            "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": cells * 24, "d2h_bytes_per_step": cells * 16,
+                    "api": "flof_optical_flow_multiscale4d_host (pinned host buffers)"},
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+            "kernels": ktab[:14]}
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            sample_res = 32 if res >= 64 else max(16, res // 2)
+            sec, kind, cores = cpu_reference_solve(sample_res)
+            scale = (res / sample_res) ** 4
+            line["cpu_baseline"] = {"value": sec * scale, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "%s CPU implementation, one full mode-1 solve on the %d^4 synthetic pair "
+                                              "(%.1f s measured), scaled x%d by cell count to %d^4"
+                                              % (kind, sample_res, sec, int(scale), res)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 96), ("cells", C.c_int64), ("launches", C.c_int), ("total_ms", C.c_float)]
+
+
+if __name__ == "__main__":
+    sys.exit(main())

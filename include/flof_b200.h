@@ -46,6 +46,7 @@ int flof_ctx_destroy(flof_ctx *ctx);
 const char *flof_last_error(flof_ctx *ctx); /* ctx may be NULL: last creation error */
 void *flof_ctx_stream(flof_ctx *ctx);       /* the cudaStream_t all work is enqueued on */
 int flof_device_count(void);
+int flof_ctx_sm_count(flof_ctx *ctx);        /* SMs of the context's device (grid sizing, tests) */
 /* number of kernels launched through this context since creation (bench.py gpu_launches) */
 long long flof_ctx_launch_count(flof_ctx *ctx);
 
@@ -57,6 +58,21 @@ int flof_memcpy_d2h(flof_ctx *ctx, void *dst, const void *src, size_t bytes); /*
 int flof_memcpy_d2d(flof_ctx *ctx, void *dst, const void *src, size_t bytes);
 int flof_memset0(flof_ctx *ctx, void *dst, size_t bytes); /* ref: Grid4d::clear grid4d.cpp:108 */
 int flof_sync(flof_ctx *ctx);
+/* pinned (page-locked) host buffers for the host<->device copies of the *_host entry points */
+int flof_host_alloc(flof_ctx *ctx, void **hptr, size_t bytes);
+int flof_host_free(flof_ctx *ctx, void *hptr);
+
+/* Per-kernel device timing with CUDA events on the context stream (no profiler involved):
+ * begin() starts bracketing every kernel launch, end() synchronises and returns one record per
+ * kernel name, sorted by total time.  Used by bench.py for the live roofline numbers. */
+typedef struct {
+	char name[96];
+	int64_t cells;   /* cells of the pyramid level the launches worked on (0 = outside the driver) */
+	int launches;
+	float total_ms;
+} flof_kernel_stat; /* one record per (kernel, level) */
+int flof_profile_begin(flof_ctx *ctx);
+int flof_profile_end(flof_ctx *ctx, flof_kernel_stat *out, int max_out, int *n_out);
 
 /* ---- element-wise Grid4d<T> ops (ref: grid4d.h:338-382, grid4d.cpp:213-264) -------------- */
 #define FLOF_OP_ADD 0  /* a += b              ref: Grid4d::add        grid4d.cpp:230 */

@@ -144,6 +144,10 @@ class Context:
         return self.lib.flof_ctx_stream(self.h)
 
     @property
+    def sm_count(self):
+        return int(self.lib.flof_ctx_sm_count(self.h))
+
+    @property
     def launches(self):
         return int(self.lib.flof_ctx_launch_count(self.h))
 

@@ -100,6 +100,7 @@ int flof_ctx_destroy(flof_ctx *ctx)
 const char *flof_last_error(flof_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
 void *flof_ctx_stream(flof_ctx *ctx) { return (void *)ctx->stream; }
 long long flof_ctx_launch_count(flof_ctx *ctx) { return ctx->launches; }
+int flof_ctx_sm_count(flof_ctx *ctx) { return ctx->sm_count; }
 
 int flof_malloc(flof_ctx *ctx, void **dptr, size_t bytes)
 {
@@ -132,6 +133,71 @@ int flof_memset0(flof_ctx *ctx, void *dst, size_t bytes)
 int flof_sync(flof_ctx *ctx)
 {
 	FLOF_CK(cudaStreamSynchronize(ctx->stream));
+	return FLOF_OK;
+}
+int flof_host_alloc(flof_ctx *ctx, void **hptr, size_t bytes)
+{
+	FLOF_ARG(hptr != NULL, "flof_host_alloc: hptr is NULL");
+	FLOF_CK(cudaMallocHost(hptr, bytes ? bytes : 16));
+	return FLOF_OK;
+}
+int flof_host_free(flof_ctx *ctx, void *hptr)
+{
+	if (hptr) FLOF_CK(cudaFreeHost(hptr));
+	return FLOF_OK;
+}
+
+int flof_profile_begin(flof_ctx *ctx)
+{
+	if (!ctx->prof_e0) {
+		ctx->prof_cap = 1 << 16;
+		ctx->prof_e0 = (cudaEvent_t *)calloc(ctx->prof_cap, sizeof(cudaEvent_t));
+		ctx->prof_e1 = (cudaEvent_t *)calloc(ctx->prof_cap, sizeof(cudaEvent_t));
+		ctx->prof_name = (const char **)calloc(ctx->prof_cap, sizeof(char *));
+		ctx->prof_cells_of = (int64_t *)calloc(ctx->prof_cap, sizeof(int64_t));
+		if (!ctx->prof_e0 || !ctx->prof_e1 || !ctx->prof_name || !ctx->prof_cells_of)
+			return flof_fail(ctx, FLOF_ERR_NOMEM, "flof_profile_begin: out of host memory");
+		for (int i = 0; i < ctx->prof_cap; ++i) {
+			FLOF_CK(cudaEventCreate(&ctx->prof_e0[i]));
+			FLOF_CK(cudaEventCreate(&ctx->prof_e1[i]));
+		}
+	}
+	ctx->prof_n = 0;
+	ctx->prof_on = 1;
+	return FLOF_OK;
+}
+int flof_profile_end(flof_ctx *ctx, flof_kernel_stat *out, int max_out, int *n_out)
+{
+	ctx->prof_on = 0;
+	FLOF_CK(cudaStreamSynchronize(ctx->stream));
+	int n = 0;
+	for (int i = 0; i < ctx->prof_n; ++i) {
+		float ms = 0.f;
+		FLOF_CK(cudaEventElapsedTime(&ms, ctx->prof_e0[i], ctx->prof_e1[i]));
+		int k = -1;
+		for (int q = 0; q < n; ++q)
+			if (out[q].cells == ctx->prof_cells_of[i] && !strncmp(out[q].name, ctx->prof_name[i], sizeof(out[q].name) - 1)) {
+				k = q;
+				break;
+			}
+		if (k < 0) {
+			if (n >= max_out) continue;
+			k = n++;
+			memset(&out[k], 0, sizeof(out[k]));
+			strncpy(out[k].name, ctx->prof_name[i], sizeof(out[k].name) - 1);
+			out[k].cells = ctx->prof_cells_of[i];
+		}
+		out[k].launches++;
+		out[k].total_ms += ms;
+	}
+	for (int a = 0; a < n; ++a)  // sort by total time, descending
+		for (int b = a + 1; b < n; ++b)
+			if (out[b].total_ms > out[a].total_ms) {
+				flof_kernel_stat t = out[a];
+				out[a] = out[b];
+				out[b] = t;
+			}
+	if (n_out) *n_out = n;
 	return FLOF_OK;
 }
 

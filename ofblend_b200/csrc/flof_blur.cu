@@ -16,6 +16,8 @@
 // weight by integer squared distance, ref gaussianWeight :128-131: exp(-dSqr/(2.*sigma*sigma))
 __constant__ float c_gauss_w[4 * FLOF_BLUR_MAXS * FLOF_BLUR_MAXS + 1];
 
+#include "flof_blur_tiled.cuh"
+
 template <class T> __device__ __forceinline__ T blur_zero();
 template <> __device__ __forceinline__ float blur_zero<float>() { return 0.f; }
 template <> __device__ __forceinline__ float4 blur_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -100,7 +102,14 @@ int flof_gaussian_blur4d_impl(flof_ctx *ctx, float *a, flof_dim4 d, int elem, fl
 	float *cur = a, *oth = (float *)tmp;
 	int rc = FLOF_OK;
 	for (int numIt = 0; numIt < 2 * iter && rc == FLOF_OK; ++numIt) {
-		if (elem == 4)
+		int tiled = 0;
+		if (elem == 4) {
+			tiled = flof_launch_gauss_tiled(ctx, cur, oth, d, s, w, numIt == 0);
+			if (tiled < 0) rc = FLOF_ERR_CUDA;
+		}
+		if (tiled != 0) {
+			// done (or failed) in the register-tiled kernel
+		} else if (elem == 4)
 			rc = launch_blur<float4>(ctx, (const float4 *)cur, (float4 *)oth, d, s);
 		else
 			rc = launch_blur<float>(ctx, cur, oth, d, s);
@@ -153,7 +162,7 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 	FLOF_RET(flof_tmp_alloc(ctx, &tmp, bytes, false));
 	float *cur = a, *oth = (float *)tmp;
 	for (int sIt = 0; sIt < sweeps; ++sIt) {
-		FLOF_LAUNCH(k_cv_expol_blur4d, flof_grid4(d), FLOF_BLOCK, 0, (const float4 *)cur, (float4 *)oth, marker, d);
+		FLOF_RET(flof_launch_expol_tiled(ctx, cur, oth, marker, d));
 		float *sw = cur; cur = oth; oth = sw;
 	}
 	int rc = FLOF_OK;

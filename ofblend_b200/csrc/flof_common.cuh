@@ -52,7 +52,28 @@ struct flof_ctx {
 	cudaEvent_t ev[4];
 	long long launches;
 	char err[512];
+	// optional per-launch CUDA-event timing (flof_profile_begin/end): bench.py uses it to measure
+	// each kernel's average duration live, outside any profiler
+	int prof_on, prof_n, prof_cap;
+	cudaEvent_t *prof_e0, *prof_e1;
+	const char **prof_name;
+	int64_t *prof_cells_of;  // per launch: cells of the grid level being processed
+	int64_t prof_cells;      // set by the multi-scale driver at each pyramid level
 };
+
+static inline int flof_prof_pre(flof_ctx *ctx, const char *name)
+{
+	if (!ctx->prof_on || ctx->prof_n >= ctx->prof_cap) return -1;
+	const int i = ctx->prof_n++;
+	ctx->prof_name[i] = name;
+	ctx->prof_cells_of[i] = ctx->prof_cells;
+	cudaEventRecord(ctx->prof_e0[i], ctx->stream);
+	return i;
+}
+static inline void flof_prof_post(flof_ctx *ctx, int i)
+{
+	if (i >= 0) cudaEventRecord(ctx->prof_e1[i], ctx->stream);
+}
 
 int flof_fail(flof_ctx *ctx, int code, const char *fmt, ...);
 
@@ -78,7 +99,9 @@ int flof_fail(flof_ctx *ctx, int code, const char *fmt, ...);
 // kernel<<<grid, block, smem, ctx->stream>>>(args) + launch accounting + error check
 #define FLOF_LAUNCH(kernel, grid, block, smem, ...)                                           \
 	do {                                                                                      \
+		const int pi__ = flof_prof_pre(ctx, #kernel);                                         \
 		kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                        \
+		flof_prof_post(ctx, pi__);                                                            \
 		ctx->launches++;                                                                      \
 		FLOF_CK(cudaGetLastError());                                                          \
 	} while (0)

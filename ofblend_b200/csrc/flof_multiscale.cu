@@ -153,6 +153,7 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 	const float projMaxDist = 4.f;
 	const float projMaxIter = 40.f;
 	const float lsDiffFac = (float)(0.1 / 20.);
+	ctx->prof_cells = n;  // tag launches with the level they work on (flof_profile_*)
 
 	DevBuf i0warped(ctx);
 	MS_RET(i0warped.alloc(rb, false));
@@ -178,6 +179,7 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 		MS_RET(flof_grid_mult_const(ctx, velSm.f(), ns, 4, half));
 		float eSm = 0.f;
 		MS_RET(multiscale(ctx, velSm.f(), i0Sm.f(), i1Sm.f(), s, P, level + 1, multiStep, doFinalProject, tr, &eSm));
+		ctx->prof_cells = n;
 		MS_RET(flof_interpol_grid_templ(ctx, vel, d, velSm.f(), s, 4));
 		const float two[4] = { 2.f, 2.f, 2.f, 2.f };
 		MS_RET(flof_grid_mult_const(ctx, vel, n, 4, two));
@@ -313,6 +315,7 @@ extern "C" int flof_optical_flow_multiscale4d(flof_ctx *ctx, float *vel, const f
 	float e = 0.f;
 	int rc = multiscale(ctx, vel, i0, i1, d, *p, 0, p->multiStep, p->doFinalProject != 0, tr, &e);
 	cudaEventRecord(ctx->ev[1], ctx->stream);
+	ctx->prof_cells = 0;
 	if (rc != FLOF_OK) return rc;
 	FLOF_CK(cudaEventSynchronize(ctx->ev[1]));
 	if (tr) cudaEventElapsedTime(&tr->total_ms, ctx->ev[0], ctx->ev[1]);

@@ -373,8 +373,85 @@ static void apply_mat(const orc_mat *m, const float *x, float *y, i64 N)
 		y[i] = v;
 	}
 }
+/* Sensitivity probe (tests only): 0 = the reference's sequential fp64 sum, 1 = the same products
+ * summed in 4096-element blocks first.  Used to measure how much the reference's own result moves
+ * when only the order of the fp64 dot-product summation changes (DESIGN.md "conditioning"). */
+static int g_dot_mode = 0;
+static int g_gpu_sms = 148; /* B200 */
+void orc_set_dot_mode(int m) { g_dot_mode = m; }
+void orc_set_gpu_sm_count(int n) { g_gpu_sms = n; }
+
+/* mode 2: the summation ORDER of the CUDA kernels (ofblend_b200/csrc/flof_solve.cu k_cg_*):
+ * 256-thread blocks, grid = min(ceil(cells/256), 8*SMs, 2048), grid-stride loop over cells, per
+ * cell the 4 component products are summed first (dot4), per-thread fp64 accumulation, warp
+ * shuffle-down tree, 8 warp sums reduced by warp 0, per-block partials summed by one block in a
+ * strided loop + the same block tree.  Same fp32 products, same fp64 adds -- only the order differs
+ * from the reference.  With this mode the oracle reproduces the GPU bit-for-bit, which isolates
+ * the summation order as the ONLY difference between the GPU path and the reference. */
+static double warp_tree(double *v) /* emulates flof_warp_sum over 32 lanes, result of lane 0 */
+{
+	for (int o = 16; o > 0; o >>= 1) {
+		double n[32];
+		for (int l = 0; l < 32; ++l) n[l] = v[l] + (l + o < 32 ? v[l + o] : v[l]);
+		for (int l = 0; l < 32; ++l) v[l] = n[l];
+	}
+	return v[0];
+}
+static double block_tree(const double *t) /* flof_block_sum for blockDim 256 */
+{
+	double sh[32];
+	for (int w = 0; w < 8; ++w) {
+		double v[32];
+		for (int l = 0; l < 32; ++l) v[l] = t[w * 32 + l];
+		sh[w] = warp_tree(v);
+	}
+	double v[32];
+	for (int l = 0; l < 32; ++l) v[l] = l < 8 ? sh[l] : 0.0;
+	return warp_tree(v);
+}
+static double dot_prod_gpu_order(const float *a, const float *b, i64 N)
+{
+	const i64 cells = N / 4;
+	i64 need = (cells + 255) / 256, cap = (i64)g_gpu_sms * 8;
+	if (cap > 2048) cap = 2048;
+	if (need < 1) need = 1;
+	const int blocks = (int)(need < cap ? need : cap);
+	const i64 T = (i64)blocks * 256;
+	double *acc = (double *)calloc((size_t)T, sizeof(double));
+	for (i64 c = 0; c < cells; ++c) {
+		const float *x = a + c * 4, *y = b + c * 4;
+		double s = (double)(x[0] * y[0]);
+		s += (double)(x[1] * y[1]);
+		s += (double)(x[2] * y[2]);
+		s += (double)(x[3] * y[3]);
+		acc[c % T] += s;
+	}
+	double *part = (double *)calloc((size_t)blocks, sizeof(double));
+	for (int bl = 0; bl < blocks; ++bl) part[bl] = block_tree(acc + (i64)bl * 256);
+	double t[256];
+	for (int th = 0; th < 256; ++th) {
+		double s = 0.;
+		for (int bl = th; bl < blocks; bl += 256) s += part[bl];
+		t[th] = s;
+	}
+	const double r = block_tree(t);
+	free(acc);
+	free(part);
+	return r;
+}
 static double dot_prod(const float *a, const float *b, i64 N)
 {
+	if (g_dot_mode == 2) return dot_prod_gpu_order(a, b, N);
+	if (g_dot_mode == 1) {
+		double tot = 0.;
+		for (i64 s = 0; s < N; s += 4096) {
+			double blk = 0.;
+			const i64 e = s + 4096 < N ? s + 4096 : N;
+			for (i64 i = s; i < e; ++i) blk += a[i] * b[i];
+			tot += blk;
+		}
+		return tot;
+	}
 	double d = 0.;
 	for (i64 i = 0; i < N; ++i) d += a[i] * b[i]; /* fp32 product, fp64 sum (:234-241) */
 	return d;

@@ -24,6 +24,10 @@ extern "C" {
 typedef struct { int nx, ny, nz, nt; } orc_dim4;
 
 int orc_set_threads(int n);
+/* CG dot-product summation order: 0 sequential (the reference), 1 blocked (conditioning probe),
+ * 2 the CUDA kernels' reduction order for a GPU with orc_set_gpu_sm_count() SMs (default 148) */
+void orc_set_dot_mode(int m);
+void orc_set_gpu_sm_count(int n);
 
 /* vector4d.h:488 interpol4d / interpol.h:101 interpol (elem = 1 or 4 floats per cell) */
 void orc_interpol4d(const float *data, orc_dim4 d, int elem, const float pos[4], float *out);

@@ -247,6 +247,10 @@ def grid_op4d(op, a, b=None, factor=0.):
     return g
 
 
+def mult_const(a, s):
+    return grid_op4d("multConst", a, None, s)
+
+
 def simple_blur_special(a, iters=1, thresh=0., bord=0):
     g = _f32(a).copy()
     lib().orc_simple_blur_special(_p(g), g.shape[2], g.shape[1], g.shape[0], int(iters),

@@ -250,6 +250,10 @@ def grid_op4d(op, a, b=None, factor=0.):
     return g
 
 
+def mult_const(a, s):
+    return grid_op4d("multConst", a, None, s)
+
+
 def _d3(a):
     return (a.shape[2], a.shape[1], a.shape[0])
 
