@@ -21,11 +21,70 @@ __constant__ float c_gauss_wsum[625];
 
 #define FLOF_TPY 4  // outputs per thread along y
 
-__device__ __forceinline__ void acc4(float4 &v, const float4 &q)
+// Blackwell packed fp32x2 arithmetic (PTX add.rn.f32x2 / mul.rn.f32x2, sm_100+): two independent
+// IEEE round-to-nearest operations per instruction -- bit-identical to scalar fp32 multiplies and
+// adds at half the issue slots.  Written as inline PTX with explicit .rn: the __fmul2_rn/__fadd2_rn
+// intrinsics of CUDA 12.9 get contracted to FFMA2 by the compiler even under -fmad=false (checked in
+// SASS), which would break parity with the reference's separately rounded multiply and add.
+struct p4 { unsigned long long lo, hi; };  // a float4 as two f32x2 register pairs
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b)
 {
-	v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+	unsigned long long r;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
 }
-__device__ __forceinline__ void wacc4(float4 &v, float w, const float4 &q)
+// w * (x, y) with two scalar multiplies, packed for the f32x2 add.  (A packed multiply cannot be
+// used: ptxas 12.9 contracts mul.rn.f32x2 -- and even fma.rn.f32x2(a, b, -0.0) -- followed by
+// add.rn.f32x2 into a single FFMA2 despite the explicit .rn and -fmad=false, verified in SASS and by
+// the bit-exactness tests; it never contracts scalar mul.rn.f32 into a packed add.)
+__device__ __forceinline__ unsigned long long f2_wmul(float w, unsigned long long q)
+{
+	float x, y;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(q));
+	const float px = __fmul_rn(w, x), py = __fmul_rn(w, y);
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(px), "f"(py));
+	return r;
+}
+__device__ __forceinline__ unsigned long long f2_splat(float w)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(w));
+	return r;
+}
+__device__ __forceinline__ p4 p4_zero()
+{
+	p4 r;
+	r.lo = 0ull;
+	r.hi = 0ull;
+	return r;
+}
+__device__ __forceinline__ p4 p4_load(const float4 *ptr)
+{
+	const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(ptr));
+	p4 r;
+	r.lo = v.x;
+	r.hi = v.y;
+	return r;
+}
+__device__ __forceinline__ float4 p4_unpack(const p4 &v)
+{
+	float4 r;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v.lo));
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(v.hi));
+	return r;
+}
+__device__ __forceinline__ void acc4(p4 &v, const p4 &q)
+{
+	v.lo = f2_add(v.lo, q.lo);
+	v.hi = f2_add(v.hi, q.hi);
+}
+__device__ __forceinline__ void wacc4(p4 &v, float w, const p4 &q)
+{
+	v.lo = f2_add(v.lo, f2_wmul(w, q.lo));
+	v.hi = f2_add(v.hi, f2_wmul(w, q.hi));
+}
+__device__ __forceinline__ void wacc4(float4 &v, float w, const float4 &q)  // scalar form (edge columns)
 {
 	v.x += w * q.x; v.y += w * q.y; v.z += w * q.z; v.w += w * q.w;
 }
@@ -48,7 +107,11 @@ static inline dim3 tiled_grid(flof_dim4 d)
 }
 
 // ------------------------------------------------------------------ 81-tap extrapolation ---
-__global__ void __launch_bounds__(FLOF_BLOCK, 3)
+// Per (vt, zk) pair the thread loads its FLOF_TPY+2 rows x 3 columns (18 independent LDG.128 in
+// flight) and then issues the 9 adds of each of its 4 outputs; row addresses are 32-bit offsets
+// computed once per thread.  Lanes on the x border and patches whose cells are all marked skip
+// the arithmetic and only copy.
+__global__ void __launch_bounds__(FLOF_BLOCK, 2)
     k_cv_expol_blur4d_tiled(const float4 *__restrict__ a, float4 *__restrict__ tmp, const float *__restrict__ mark,
                             flof_dim4 d)
 {
@@ -67,28 +130,37 @@ __global__ void __launch_bounds__(FLOF_BLOCK, 3)
 		need[oy] = n;
 		any |= n;
 	}
-	float4 acc[FLOF_TPY];
+	p4 acc[FLOF_TPY];
 #pragma unroll
-	for (int oy = 0; oy < FLOF_TPY; ++oy) acc[oy] = make_float4(0.f, 0.f, 0.f, 0.f);
-	if (any) {  // (whole warps of marked / border cells skip the arithmetic)
-		const int xm = max(x - 1, 0), xp = min(x + 1, d.nx - 1);
-		for (int vt = t - 1; vt <= t + 1; ++vt)
-			for (int zk = k - 1; zk <= k + 1; ++zk) {
-				const float4 *base = a + flof_idx(d, 0, 0, zk, vt);
+	for (int oy = 0; oy < FLOF_TPY; ++oy) acc[oy] = p4_zero();
+	if (any) {  // col_in holds: x-1 and x+1 are inside the grid
+		int roff[FLOF_TPY + 2];  // offset of (x, clamp(y0-1+r)) inside a z-t plane
+#pragma unroll
+		for (int r = 0; r < FLOF_TPY + 2; ++r) roff[r] = min(max(y0 - 1 + r, 0), d.ny - 1) * d.nx + x;
+		const int64_t sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
+		for (int vt = t - 1; vt <= t + 1; ++vt) {
+			const float4 *base = a + (sT * vt + sZ * (k - 1));
+#pragma unroll 1
+			for (int zk = 0; zk < 3; ++zk, base += sZ) {
+				p4 L[FLOF_TPY + 2][3];
 #pragma unroll
 				for (int r = 0; r < FLOF_TPY + 2; ++r) {
-					const int yj = min(max(y0 - 1 + r, 0), d.ny - 1);
-					const float4 *row = base + (int64_t)yj * d.nx;
-					const float4 l0 = __ldg(row + xm), l1 = __ldg(row + x), l2 = __ldg(row + xp);
+					const float4 *row = base + roff[r];
+					L[r][0] = p4_load(row - 1);
+					L[r][1] = p4_load(row);
+					L[r][2] = p4_load(row + 1);
+				}
+#pragma unroll
+				for (int r = 0; r < FLOF_TPY + 2; ++r)
 #pragma unroll
 					for (int oy = 0; oy < FLOF_TPY; ++oy) {
 						if (r < oy || r > oy + 2) continue;
-						acc4(acc[oy], l0);
-						acc4(acc[oy], l1);
-						acc4(acc[oy], l2);
+						acc4(acc[oy], L[r][0]);
+						acc4(acc[oy], L[r][1]);
+						acc4(acc[oy], L[r][2]);
 					}
-				}
 			}
+		}
 	}
 	const double f = 1. / 81.0;
 #pragma unroll
@@ -97,7 +169,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK, 3)
 		if (y >= d.ny) continue;
 		const int64_t c = plane + (int64_t)y * d.nx + x;
 		if (need[oy]) {
-			const float4 v = acc[oy];
+			const float4 v = p4_unpack(acc[oy]);
 			tmp[c] = make_float4((float)(v.x * f), (float)(v.y * f), (float)(v.z * f), (float)(v.w * f));
 		} else {
 			tmp[c] = __ldg(a + c);
@@ -118,6 +190,11 @@ template <int S> __device__ __forceinline__ int clip_state(int i, int n)
 	return lo > 0 ? lo : (hi > 0 ? S + hi : 0);
 }
 
+// Fast path: outputs whose x window is complete (S <= x < nx-S), so the 2S+1 column loads of a row
+// are plain unit-stride loads at immediate offsets and need no masking; rows outside the grid are
+// skipped with a (warp-uniform) branch, t/z slabs outside with the loop `continue`.  The (S+1)^2
+// distinct weights of a (vt, zk) pair are fetched once into registers.  The 2(S-1) remaining
+// interior columns next to the x border are done by k_gauss_blur4d_cols (generic arithmetic).
 template <int S>
 __global__ void __launch_bounds__(FLOF_BLOCK, 3)
     k_gauss_blur4d_tiled(const float4 *__restrict__ a, float4 *__restrict__ tmp, flof_dim4 d)
@@ -127,62 +204,98 @@ __global__ void __launch_bounds__(FLOF_BLOCK, 3)
 	if (!tiled_xy(d, x, y0)) return;
 	const int k = (int)blockIdx.y, t = (int)blockIdx.z;
 	if (k < 1 || k >= d.nz - 1 || t < 1 || t >= d.nt - 1) return;  // KERNEL(fourd, bnd = 1)
-	if (x < 1 || x >= d.nx - 1) return;
-	int xs[NS];
-	bool xin[NS];
+	if (x < S || x >= d.nx - S) return;                            // x-border columns: other kernel
+	p4 acc[FLOF_TPY];
 #pragma unroll
-	for (int q = 0; q < NS; ++q) {
-		const int xi = x - S + q;
-		xin[q] = xi >= 0 && xi < d.nx;
-		xs[q] = min(max(xi, 0), d.nx - 1);
-	}
-	const bool edge = !(xin[0] && xin[NS - 1]);
-	float4 acc[FLOF_TPY];
-#pragma unroll
-	for (int oy = 0; oy < FLOF_TPY; ++oy) acc[oy] = make_float4(0.f, 0.f, 0.f, 0.f);
+	for (int oy = 0; oy < FLOF_TPY; ++oy) acc[oy] = p4_zero();
+	const int64_t sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
+	const int xoff = (y0 - S) * d.nx + x;  // may be negative: only dereferenced for rows inside the grid
 
+	for (int vt = t - S; vt <= t + S; ++vt) {
+		if (vt < 0 || vt >= d.nt) continue;
+		const int dt2 = (vt - t) * (vt - t);
+#pragma unroll 1
+		for (int zk = k - S; zk <= k + S; ++zk) {
+			if (zk < 0 || zk >= d.nz) continue;
+			const int dz2 = dt2 + (zk - k) * (zk - k);
+			float w[S + 1][S + 1];
+#pragma unroll
+			for (int p = 0; p <= S; ++p)
+#pragma unroll
+				for (int q = 0; q <= S; ++q) w[p][q] = c_gauss_w[dz2 + p * p + q * q];
+			const float4 *base = a + (sT * vt + sZ * zk) + xoff;
+#pragma unroll
+			for (int r = 0; r < FLOF_TPY + 2 * S; ++r) {
+				const int yj = y0 - S + r;
+				if (yj < 0 || yj >= d.ny) continue;
+				const float4 *row = base + r * d.nx;
+				p4 L[NS];
+#pragma unroll
+				for (int q = 0; q < NS; ++q) L[q] = p4_load(row + (q - S));
+#pragma unroll
+				for (int oy = 0; oy < FLOF_TPY; ++oy) {
+					const int dy = r - S - oy;
+					if (dy < -S || dy > S) continue;
+#pragma unroll
+					for (int q = 0; q < NS; ++q) wacc4(acc[oy], w[dy < 0 ? -dy : dy][q < S ? S - q : q - S], L[q]);
+				}
+			}
+		}
+	}
+	const int st = clip_state<S>(t, d.nt), sz = clip_state<S>(k, d.nz);
+#pragma unroll
+	for (int oy = 0; oy < FLOF_TPY; ++oy) {
+		const int y = y0 + oy;
+		if (y < 1 || y >= d.ny - 1) continue;
+		const int64_t c = flof_idx(d, x, y, k, t);
+		const float weight = c_gauss_wsum[((st * NS + sz) * NS + clip_state<S>(y, d.ny)) * NS];  // sx = 0
+		const float4 v = p4_unpack(acc[oy]);
+		if (weight > FLOF_VECTOR_EPSILON)
+			tmp[c] = make_float4(v.x / weight, v.y / weight, v.z / weight, v.w / weight);
+		else
+			tmp[c] = __ldg(a + c);
+	}
+}
+
+// interior columns whose x window is clipped: 1 <= x < S and nx-S <= x < nx-1 (none for S = 1).
+// One thread per cell, the generic tap loop of flof_blur.cu.
+template <int S>
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_gauss_blur4d_cols(const float4 *__restrict__ a, float4 *__restrict__ tmp, flof_dim4 d)
+{
+	constexpr int NC = 2 * (S - 1);
+	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
+	if (NC == 0 || p >= (unsigned)(NC * d.ny)) return;
+	const int j = (int)(p / (unsigned)NC), ci = (int)(p - (unsigned)j * NC);
+	const int i = ci < S - 1 ? 1 + ci : d.nx - S + (ci - (S - 1));
+	const int k = (int)blockIdx.y, t = (int)blockIdx.z;
+	if (!flof_in_bounds(d, i, j, k, t, 1)) return;
+	float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+	float weight = 0.f;
+	const int x0 = max(i - S, 0), x1 = min(i + S, d.nx - 1);
 	for (int vt = t - S; vt <= t + S; ++vt) {
 		if (vt < 0 || vt >= d.nt) continue;
 		const int dt2 = (vt - t) * (vt - t);
 		for (int zk = k - S; zk <= k + S; ++zk) {
 			if (zk < 0 || zk >= d.nz) continue;
 			const int dz2 = dt2 + (zk - k) * (zk - k);
-			const float4 *base = a + flof_idx(d, 0, 0, zk, vt);
-#pragma unroll
-			for (int r = 0; r < FLOF_TPY + 2 * S; ++r) {
-				const int yj = y0 - S + r;
+			for (int yj = j - S; yj <= j + S; ++yj) {
 				if (yj < 0 || yj >= d.ny) continue;
-				const float4 *row = base + (int64_t)yj * d.nx;
-				float4 L[NS];
-#pragma unroll
-				for (int q = 0; q < NS; ++q) L[q] = __ldg(row + xs[q]);
-#pragma unroll
-				for (int oy = 0; oy < FLOF_TPY; ++oy) {
-					const int dy = r - S - oy;
-					if (dy < -S || dy > S) continue;
-					const int by = dz2 + dy * dy;
-#pragma unroll
-					for (int q = 0; q < NS; ++q) {
-						if (edge && !xin[q]) continue;
-						wacc4(acc[oy], c_gauss_w[by + (q - S) * (q - S)], L[q]);
-					}
+				const int dy2 = dz2 + (yj - j) * (yj - j);
+				const float4 *row = a + flof_idx(d, 0, yj, zk, vt);
+				for (int xi = x0; xi <= x1; ++xi) {
+					const float wcurr = c_gauss_w[dy2 + (xi - i) * (xi - i)];
+					weight += wcurr;
+					wacc4(val, wcurr, __ldg(row + xi));
 				}
 			}
 		}
 	}
-	const int st = clip_state<S>(t, d.nt), sz = clip_state<S>(k, d.nz), sx = clip_state<S>(x, d.nx);
-#pragma unroll
-	for (int oy = 0; oy < FLOF_TPY; ++oy) {
-		const int y = y0 + oy;
-		if (y < 1 || y >= d.ny - 1) continue;
-		const int64_t c = flof_idx(d, x, y, k, t);
-		const float weight = c_gauss_wsum[((st * NS + sz) * NS + clip_state<S>(y, d.ny)) * NS + sx];
-		const float4 v = acc[oy];
-		if (weight > FLOF_VECTOR_EPSILON)
-			tmp[c] = make_float4(v.x / weight, v.y / weight, v.z / weight, v.w / weight);
-		else
-			tmp[c] = __ldg(a + c);
-	}
+	const int64_t c = flof_idx(d, i, j, k, t);
+	if (weight > FLOF_VECTOR_EPSILON)
+		tmp[c] = make_float4(val.x / weight, val.y / weight, val.z / weight, val.w / weight);
+	else
+		tmp[c] = __ldg(a + c);
 }
 
 // host: weight sums for every clip state, accumulated in the reference's tap order (:138-151)
@@ -231,6 +344,13 @@ int flof_launch_gauss_tiled(flof_ctx *ctx, const float *a, float *tmp, flof_dim4
 		k_gauss_blur4d_tiled<2><<<tiled_grid(d), FLOF_BLOCK, 0, ctx->stream>>>((const float4 *)a, (float4 *)tmp, d);
 	flof_prof_post(ctx, pi);
 	ctx->launches++;
+	if (s == 2) {
+		const int pj = flof_prof_pre(ctx, "k_gauss_blur4d_cols<2>");
+		dim3 g((unsigned)((2 * d.ny + FLOF_BLOCK - 1) / FLOF_BLOCK), (unsigned)d.nz, (unsigned)d.nt);
+		k_gauss_blur4d_cols<2><<<g, FLOF_BLOCK, 0, ctx->stream>>>((const float4 *)a, (float4 *)tmp, d);
+		flof_prof_post(ctx, pj);
+		ctx->launches++;
+	}
 	if (cudaGetLastError() != cudaSuccess) return flof_fail(ctx, FLOF_ERR_CUDA, "k_gauss_blur4d_tiled launch failed"), -1;
 	return 1;
 }

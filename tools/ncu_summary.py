@@ -29,13 +29,15 @@ def main(path):
             if w in hdr:
                 i = hdr.index(w)
                 print('  %-68s %18s %s' % (w, r[i][:18], units[i]))
+        st = []
         for i, h in enumerate(hdr):
-            if 'warp_issue_stalled' in h and h.endswith('_per_warp_active.pct'):
+            if 'issue_stalled' in h and 'not_issued' not in h:
                 try:
-                    if float(r[i]) >= 8.0:
-                        print('  stall %-62s %18s %%' % (h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_warp_active.pct', ''), r[i][:8]))
+                    st.append((float(r[i]), h, units[i]))
                 except ValueError:
                     pass
+        for v, h, u in sorted(st, reverse=True)[:7]:
+            print('  stall %-62s %18.3f %s' % (h.replace('smsp__average_warp', '').replace('smsp__', '')[:62], v, u))
 
 
 if __name__ == '__main__':
