@@ -9,6 +9,8 @@ Dev container only.  Procedure:
 so that modes 2/3 are compared on bit-identical deformation input.
 Stores sub-sampled reference outputs in tests/golden/scene_flof.npz.
     python tests/golden/make_scene_golden.py /tmp/scenesyn /tmp/scenesyn2
+README configuration (BASELINE.json configs[0..2]; inputs from the reference's dataGen2Drop.py px {0,1}):
+    python tests/golden/make_scene_golden.py /tmp/flofdata /tmp/flofdata scene_readme.npz
 """
 import glob
 import os
@@ -42,7 +44,7 @@ def frames(d, prefix, pick):
     return nums, out
 
 
-def main(da, db):
+def main(da, db, outname="scene_flof.npz"):
     g = {}
     for tag, fn, log in (("01", "defo01_000_001_032_vel.uni", "ref_mode1_01.log"), ("10", "defo01_001_000_032_vel.uni", "ref_mode1_10.log")):
         v = uni.read_uni(os.path.join(da, fn))
@@ -53,13 +55,15 @@ def main(da, db):
         g["m1_%s_errs" % tag] = er
         g["m1_%s_input_err" % tag] = inp
     for tag, prefix in (("m2", "out_f0t1_a100"), ("m2tw", "out_f0t1_a030"), ("m3", "out_f0t1_a050")):
+        if not glob.glob(os.path.join(db, prefix + "_[0-9][0-9][0-9][0-9].uni")):
+            continue
         nums, fr = frames(db, prefix, (0.0, 0.35, 0.7, 1.0))
         g["%s_frame_numbers" % tag] = np.array(nums, np.int32)
         for n, a in fr.items():
             g["%s_frame_%04d" % (tag, n)] = a if a.size <= 70000 else a[::2, ::2, ::2].copy()
-    np.savez_compressed(os.path.join(HERE, "scene_flof.npz"), **g)
+    np.savez_compressed(os.path.join(HERE, outname), **g)
     print({k: (v.shape if hasattr(v, "shape") else v) for k, v in g.items()})
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(*sys.argv[1:4])

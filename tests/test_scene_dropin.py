@@ -93,3 +93,38 @@ def test_mode2_mode3_scene(inputs):
     _check_frames(inputs, g, "m2tw", "out_f0t1_a030", 1e-3)
     run_flof(inputs, "mode", 3, "twoway", 1, "alpha", 50, "writeuni", 1)
     _check_frames(inputs, g, "m3", "out_f0t1_a050", 1e-3)
+
+
+README_DATA = os.path.join(ROOT, "oracle", "_ref", "data", "readme")
+README_GOLD = os.path.join(ROOT, "tests", "golden", "scene_readme.npz")
+
+
+@pytest.mark.skipif(not os.path.isdir(README_DATA) or not os.path.isfile(README_GOLD),
+                    reason="README data set (oracle/_ref/data/readme, generated by the reference's dataGen2Drop.py) missing")
+def test_readme_configuration(tmp_path):
+    """BASELINE.json configs[0..2] on the reference's own example data (dataGen2Drop.py px 0/1, res 40):
+    mode 1 default run (+ reverse), mode 2 and mode 3 two-way alpha 50, all through the unmodified flof.py."""
+    from ofblend_b200 import uni
+    g = np.load(README_GOLD)
+    d = str(tmp_path)
+    for f in os.listdir(README_DATA):
+        if not f.startswith("ref_"):
+            os.symlink(os.path.join(README_DATA, f), os.path.join(d, f))
+    for tag, a0, a1, fn in (("01", 0, 1, "defo01_000_001_032_vel.uni"), ("10", 1, 0, "defo01_001_000_032_vel.uni")):
+        out = run_flof(d, "dataid0", a0, "dataid1", a1, "mode", 1)
+        iters = [int(x) for x in re.findall(r"ofSolve fix iterations:(\d+)", out)]
+        errs = [float(x) for x in re.findall(r"Current error, step \d+ = ([0-9.eE+-]+)", out)]
+        inp = [float(x) for x in re.findall(r"Error between inputs ([0-9.eE+-]+)", out)]
+        assert iters == [int(x) for x in g["m1_%s_iters" % tag]], (iters, g["m1_%s_iters" % tag])   # 27,25,24,27,27,27 (SURVEY §6)
+        assert np.allclose(inp, g["m1_%s_input_err" % tag], rtol=1e-5)                              # 350.4529
+        assert np.allclose(errs, g["m1_%s_errs" % tag][:-1], rtol=1e-4), (errs, g["m1_%s_errs" % tag])
+        vel = uni.read_uni(os.path.join(d, fn))
+        assert rel_l2(vel[::2, ::2, ::2, ::2], g["m1_%s_vel_sub" % tag]) <= 1e-2     # conditioning band, DESIGN.md §2
+        os.remove(os.path.join(d, fn))
+    # modes 2 / 3 on the reference's own deformation files: applied SDF within 1e-3 cells
+    for a, b in (("000_001", "ref_defo01_000_001_032_vel.uni"), ("001_000", "ref_defo01_001_000_032_vel.uni")):
+        os.symlink(os.path.join(README_DATA, b), os.path.join(d, "defo01_%s_032_vel.uni" % a))
+    run_flof(d, "dataid0", 0, "dataid1", 1, "mode", 2, "writeuni", 1)
+    _check_frames(d, g, "m2", "out_f0t1_a100", 1e-3)
+    run_flof(d, "mode", 3, "twoway", 1, "alpha", 50, "writeuni", 1)
+    _check_frames(d, g, "m3", "out_f0t1_a050", 1e-3)
