@@ -161,18 +161,12 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     from ofblend_b200 import capi, synth
-    ctx = capi.Context(local_rank)
+    from ofblend_b200 import dist as fdist
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # one process per GPU; the NCCL communicator lives inside libflof_b200.so (ofblend_b200/dist.py)
+    ctx, rank, world = fdist.init()
     api = capi.HostAPI(ctx)
     res = args.res
     dims = (res, res, res, res)
@@ -188,9 +182,7 @@ def main():
     zero4 = np.zeros(4, np.float32)
 
     def barrier():
-        ctx.sync()
-        if dist is not None:
-            dist.barrier()
+        fdist.barrier(ctx)  # stream synchronise + NCCL barrier over all ranks
 
     def one_step():
         ctx.grid_set_const(vel, zero4)
@@ -219,12 +211,7 @@ def main():
     launches = ctx.launches - launches0
 
     # device time (CUDA events on the library's stream, recorded inside the call); max over ranks
-    ms_per_step = dev_ms / args.steps
-    if dist is not None:
-        import torch
-        tmax = torch.tensor([ms_per_step], device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms_per_step = float(tmax.item())
+    ms_per_step = fdist.max_over_ranks(ctx, dev_ms / args.steps)
 
     # ---- e2e: host buffers through the plugin-level C-ABI call, copies inside the timed region
     hb = {}
@@ -247,12 +234,7 @@ def main():
         barrier()
         if s > 0:
             e2e_times.append(time.perf_counter() - t1)
-    e2e_s = float(np.mean(e2e_times))
-    if dist is not None:
-        import torch
-        tmax = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_s = float(tmax.item())
+    e2e_s = fdist.max_over_ranks(ctx, float(np.mean(e2e_times)))
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -275,13 +257,16 @@ def main():
                "ms_per_step": stats[q].total_ms / prof_steps, "avg_launch_ms": stats[q].total_ms / stats[q].launches,
                "share": stats[q].total_ms / max(tot_ms, 1e-9)}
         if key is not None and stats[q].cells > 0:
-            row["bytes_per_launch"] = KERNEL_BYTES_PER_CELL[key] * int(stats[q].cells)
+            # a sharded level is cut along t: each rank's launch covers cells / world of the level
+            sharded = world > 1 and int(stats[q].cells) >= (1 << 20)
+            row["cells_per_launch"] = int(stats[q].cells) // (world if sharded else 1)
+            row["bytes_per_launch"] = KERNEL_BYTES_PER_CELL[key] * row["cells_per_launch"]
             row["gbs"] = row["bytes_per_launch"] / (row["avg_launch_ms"] * 1e-3) / 1e9
             row["frac"] = row["gbs"] / peak
         ktab.append(row)
     dom = next((r for r in ktab if "gbs" in r), None)  # ktab is sorted by total time: dominant (kernel, level)
     if dom is not None:
-        roofline = {"bound": "hbm", "kernel": dom["kernel"], "cells_per_launch": dom["cells"], "achieved": dom["gbs"],
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "cells_per_launch": dom["cells_per_launch"], "achieved": dom["gbs"],
                     "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
                     "bytes_per_launch": dom["bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
                     "share_of_step": dom["share"],
@@ -291,13 +276,13 @@ def main():
 
     line = {"metric": METRIC, "value": ms_per_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
-            "scaling": "strong" if world == 1 else "replicas", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "flof mode 1 (opticalFlowMultiscale4d, README parameters: wSmooth 1e-3, wEnergy 1e-4, "
                                    "cgAccuracy 1e-2, postVelBlur 4, multiStep 3, minGridSize 20, final projection) on "
                                    "synthetic two-drop 4D SDF pair %d^4" % res,
                        "res": res, "levels": [res >> l for l in range(8) if (res >> l) > 10 and (l == 0 or (res >> (l - 1)) > 20)],
                        "l2": "working set (%d MB of grids) exceeds the 126 MB L2; no explicit flush" % (cells * 4 * 30 // 2 ** 20),
-                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (t-sharding: next round)" % world},
+                       "parallelism": "1 GPU" if world == 1 else "t-sharded over %d GPUs (levels >= 2^20 cells; NCCL halos + all-reduce)" % world},
             "wall_ms_per_step": wall / args.steps * 1e3,
             "cg_cell_updates_per_s": cg_updates / max(cg_ms * 1e-3, 1e-12),
             "cg_iters": [int(trace.cg_iters[q]) for q in range(min(trace.n_solves, 64))],
@@ -309,7 +294,7 @@ def main():
             "roofline": roofline,
             "kernels": ktab[:14]}
     if rank == 0:
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             sample_res = 32 if res >= 64 else max(16, res // 2)
             sec, kind, cores = cpu_reference_solve(sample_res)
             scale = (res / sample_res) ** 4
@@ -318,9 +303,8 @@ def main():
                                               "(%.1f s measured), scaled x%d by cell count to %d^4"
                                               % (kind, sample_res, sec, int(scale), res)}
         print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    barrier()
+    ctx.close()
     return 0
 
 

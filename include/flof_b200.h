@@ -74,6 +74,23 @@ typedef struct {
 int flof_profile_begin(flof_ctx *ctx);
 int flof_profile_end(flof_ctx *ctx, flof_kernel_stat *out, int max_out, int *n_out);
 
+/* ---- multi-GPU (one process + one context per GPU, NCCL over NVLink; the reference is single process) ----
+ * t-sharding: inside flof_optical_flow_multiscale4d every pyramid level whose T is divisible
+ * by the rank count (and large enough) is cut along t; ranks own T/P contiguous slices, exchange ghost
+ * slices per stencil sweep, all-reduce the CG scalars and all-gather gather sources.  Inputs must be
+ * identical (replicated) on every rank at call time; the returned deformation is complete on every rank. */
+#define FLOF_COMM_ID_BYTES 128
+int flof_comm_unique_id(char out[FLOF_COMM_ID_BYTES]);  /* rank 0: ncclGetUniqueId, distribute out of band */
+int flof_ctx_comm_init(flof_ctx *ctx, int nranks, int rank, const char id[FLOF_COMM_ID_BYTES]);
+int flof_ctx_comm_destroy(flof_ctx *ctx);
+int flof_ctx_rank(flof_ctx *ctx);
+int flof_ctx_nranks(flof_ctx *ctx);
+/* levels with fewer cells are computed redundantly on every rank instead of being sharded (default 2^20) */
+int flof_ctx_set_shard_min_cells(flof_ctx *ctx, int64_t cells);
+void flof_slab_range(int nt, int nranks, int rank, int *ta, int *tb); /* slices owned by `rank` */
+int flof_comm_barrier(flof_ctx *ctx);                                 /* stream sync + all ranks */
+int flof_comm_allreduce_max_host(flof_ctx *ctx, double *v);           /* max over ranks of a host scalar */
+
 /* ---- element-wise Grid4d<T> ops (ref: grid4d.h:338-382, grid4d.cpp:213-264) -------------- */
 #define FLOF_OP_ADD 0  /* a += b              ref: Grid4d::add        grid4d.cpp:230 */
 #define FLOF_OP_SUB 1  /* a -= b              ref: Grid4d::sub        grid4d.cpp:234 */

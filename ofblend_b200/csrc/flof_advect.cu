@@ -19,7 +19,7 @@ template <> __device__ __forceinline__ float4 zero_of<float4>() { return make_fl
 template <class T>
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_semi_lagrange4d(const float4 *__restrict__ vel, const T *__restrict__ src, T *__restrict__ dst,
-                      flof_dim4 d, float dt)
+                      flof_kd d, float dt)
 {
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t)) return;
@@ -41,12 +41,14 @@ extern "C" int flof_semi_lagrange4d(flof_ctx *ctx, const float *vel, const float
 	FLOF_ARG(elem == 1 || elem == 4, "advect4d: Grid Type is not supported (only Real, Vec4)");
 	FLOF_ARG(src != dst, "flof_semi_lagrange4d: dst must not alias src");
 	FLOF_ARG(d.nx >= 2 && d.ny >= 2 && d.nz >= 2 && d.nt >= 2, "advect4d: grid too small");
+	// sharded level: dst and vel are touched on this rank's slices only; src must be complete (the
+	// back-traced positions leave the slab), see flof_advect_cfl4d_ex
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
 	if (elem == 4)
-		FLOF_LAUNCH(k_semi_lagrange4d<float4>, flof_grid4(d), FLOF_BLOCK, 0, (const float4 *)vel,
-		            (const float4 *)src, (float4 *)dst, d, dt);
+		FLOF_LAUNCH(k_semi_lagrange4d<float4>, g, FLOF_BLOCK, 0, (const float4 *)vel, (const float4 *)src, (float4 *)dst, kd, dt);
 	else
-		FLOF_LAUNCH(k_semi_lagrange4d<float>, flof_grid4(d), FLOF_BLOCK, 0, (const float4 *)vel, src,
-		            dst, d, dt);
+		FLOF_LAUNCH(k_semi_lagrange4d<float>, g, FLOF_BLOCK, 0, (const float4 *)vel, src, dst, kd, dt);
 	return FLOF_OK;
 }
 
@@ -72,8 +74,20 @@ __global__ void k_scale_vec4(const float4 *__restrict__ src, float4 *__restrict_
 	}
 }
 
+int flof_advect_cfl4d_ex(flof_ctx *ctx, float cfl, const float *vel, float *grid, flof_dim4 d, int elem,
+                         float velFactor, int grid_complete);
+
 extern "C" int flof_advect_cfl4d(flof_ctx *ctx, float cfl, const float *vel, float *grid,
                                  flof_dim4 d, int elem, float velFactor)
+{
+	return flof_advect_cfl4d_ex(ctx, cfl, vel, grid, d, elem, velFactor, 0);
+}
+
+// grid_complete: on a sharded level, `grid` is known to hold valid data on ALL slices (e.g. a fresh
+// copy of an input), so no all-gather is needed before the first gather pass.  The result is valid
+// on this rank's slices only.
+int flof_advect_cfl4d_ex(flof_ctx *ctx, float cfl, const float *vel, float *grid, flof_dim4 d, int elem,
+                         float velFactor, int grid_complete)
 {
 	FLOF_ARG(elem == 1 || elem == 4, "advect4d: Grid Type is not supported (only Real, Vec4)");
 	const int64_t cells = flof_cells(d);
@@ -83,8 +97,10 @@ extern "C" int flof_advect_cfl4d(flof_ctx *ctx, float cfl, const float *vel, flo
 	void *velTmp = NULL;
 	if (velFactor != 1.0f) {
 		FLOF_RET(flof_tmp_alloc(ctx, &velTmp, sizeof(float) * 4 * (size_t)cells, false));
-		FLOF_LAUNCH(k_scale_vec4, flof_flat_blocks(ctx, cells, 8), FLOF_BLOCK, 0, (const float4 *)vel,
-		            (float4 *)velTmp, cells, velFactor);
+		int64_t c0, c1;
+		flof_flat_range(ctx, cells, &c0, &c1);
+		FLOF_LAUNCH(k_scale_vec4, flof_flat_blocks(ctx, c1 - c0, 8), FLOF_BLOCK, 0, (const float4 *)vel + c0,
+		            (float4 *)velTmp + c0, c1 - c0, velFactor);
 		v = (const float *)velTmp;
 	}
 	// ref :1311-1316: maxVel = getMaxValue()*dt; steps = int(maxVel/cfl)+1; dt = 1/steps
@@ -103,8 +119,10 @@ extern "C" int flof_advect_cfl4d(flof_ctx *ctx, float cfl, const float *vel, flo
 	FLOF_RET(flof_tmp_alloc(ctx, &fwd, gbytes, false));
 	float *cur = grid, *nxt = (float *)fwd;
 	int rc = FLOF_OK;
+	const size_t slice_bytes = sizeof(float) * (size_t)elem * (size_t)d.nx * d.ny * d.nz;
 	for (int s = 0; s < steps && rc == FLOF_OK; ++s) {
-		rc = flof_semi_lagrange4d(ctx, v, cur, nxt, d, elem, dt * 1.f);
+		if (!(s == 0 && grid_complete)) rc = flof_allgather_slabs(ctx, cur, d.nt, slice_bytes);
+		if (rc == FLOF_OK) rc = flof_semi_lagrange4d(ctx, v, cur, nxt, d, elem, dt * 1.f);
 		float *sw = cur; cur = nxt; nxt = sw;
 	}
 	if (rc == FLOF_OK && cur != grid) rc = flof_memcpy_d2d(ctx, grid, cur, gbytes);

@@ -67,6 +67,9 @@ int flof_ctx_create(flof_ctx **out, int device)
 		return FLOF_ERR_CUDA;
 	}
 	c->sm_count = prop.multiProcessorCount;
+	c->nranks = 1;
+	c->rank = 0;
+	c->shard_min_cells = (int64_t)1 << 20;
 	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CCK(cudaDeviceGetDefaultMemPool(&c->pool, device));
 	uint64_t thr = UINT64_MAX;
@@ -88,6 +91,7 @@ int flof_ctx_destroy(flof_ctx *ctx)
 	if (!ctx) return FLOF_OK;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	flof_ctx_comm_destroy(ctx);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
 	cudaFreeHost(ctx->pinned);
 	cudaFree(ctx->cg);
@@ -101,6 +105,11 @@ const char *flof_last_error(flof_ctx *ctx) { return ctx ? ctx->err : g_create_er
 void *flof_ctx_stream(flof_ctx *ctx) { return (void *)ctx->stream; }
 long long flof_ctx_launch_count(flof_ctx *ctx) { return ctx->launches; }
 int flof_ctx_sm_count(flof_ctx *ctx) { return ctx->sm_count; }
+int flof_ctx_set_shard_min_cells(flof_ctx *ctx, int64_t cells)
+{
+	ctx->shard_min_cells = cells;
+	return FLOF_OK;
+}
 
 int flof_malloc(flof_ctx *ctx, void **dptr, size_t bytes)
 {

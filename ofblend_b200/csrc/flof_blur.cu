@@ -37,7 +37,7 @@ __device__ __forceinline__ float4 blur_div(const float4 &v, float w)
 // after pass 2 (ref :160-174) because the caller ping-pongs the same two buffers.
 template <class T, int S>
 __global__ void __launch_bounds__(FLOF_BLOCK)
-    k_gauss_blur4d(const T *__restrict__ a, T *__restrict__ tmp, flof_dim4 d)
+    k_gauss_blur4d(const T *__restrict__ a, T *__restrict__ tmp, flof_kd d)
 {
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t)) return;
@@ -73,11 +73,13 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 template <class T>
 static int launch_blur(flof_ctx *ctx, const T *a, T *tmp, flof_dim4 d, int s)
 {
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
 	switch (s) {
-	case 1: FLOF_LAUNCH((k_gauss_blur4d<T, 1>), flof_grid4(d), FLOF_BLOCK, 0, a, tmp, d); break;
-	case 2: FLOF_LAUNCH((k_gauss_blur4d<T, 2>), flof_grid4(d), FLOF_BLOCK, 0, a, tmp, d); break;
-	case 3: FLOF_LAUNCH((k_gauss_blur4d<T, 3>), flof_grid4(d), FLOF_BLOCK, 0, a, tmp, d); break;
-	case 4: FLOF_LAUNCH((k_gauss_blur4d<T, 4>), flof_grid4(d), FLOF_BLOCK, 0, a, tmp, d); break;
+	case 1: FLOF_LAUNCH((k_gauss_blur4d<T, 1>), g, FLOF_BLOCK, 0, a, tmp, kd); break;
+	case 2: FLOF_LAUNCH((k_gauss_blur4d<T, 2>), g, FLOF_BLOCK, 0, a, tmp, kd); break;
+	case 3: FLOF_LAUNCH((k_gauss_blur4d<T, 3>), g, FLOF_BLOCK, 0, a, tmp, kd); break;
+	case 4: FLOF_LAUNCH((k_gauss_blur4d<T, 4>), g, FLOF_BLOCK, 0, a, tmp, kd); break;
 	default: return flof_fail(ctx, FLOF_ERR_ARG, "gaussianBlur: kernel half-width %d > %d unsupported", s, FLOF_BLUR_MAXS);
 	}
 	return FLOF_OK;
@@ -101,7 +103,10 @@ int flof_gaussian_blur4d_impl(flof_ctx *ctx, float *a, flof_dim4 d, int elem, fl
 	FLOF_RET(flof_tmp_alloc(ctx, &tmp, bytes, true));  // GRID tmp(parent): zero-initialised
 	float *cur = a, *oth = (float *)tmp;
 	int rc = FLOF_OK;
+	const size_t slice_bytes = sizeof(float) * (size_t)elem * (size_t)d.nx * d.ny * d.nz;
 	for (int numIt = 0; numIt < 2 * iter && rc == FLOF_OK; ++numIt) {
+		rc = flof_halo_exchange(ctx, cur, d.nt, slice_bytes, s);  // sharded level: +-s ghost slices of the source
+		if (rc != FLOF_OK) break;
 		int tiled = 0;
 		if (elem == 4) {
 			tiled = flof_launch_gauss_tiled(ctx, cur, oth, d, s, w, numIt == 0);
@@ -161,7 +166,9 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 	void *tmp = NULL;
 	FLOF_RET(flof_tmp_alloc(ctx, &tmp, bytes, false));
 	float *cur = a, *oth = (float *)tmp;
+	const size_t slice_bytes = sizeof(float) * 4 * (size_t)d.nx * d.ny * d.nz;
 	for (int sIt = 0; sIt < sweeps; ++sIt) {
+		FLOF_RET(flof_halo_exchange(ctx, cur, d.nt, slice_bytes, 1));  // sharded level: +-1 ghost slice per sweep
 		FLOF_RET(flof_launch_expol_tiled(ctx, cur, oth, marker, d));
 		float *sw = cur; cur = oth; oth = sw;
 	}
@@ -173,7 +180,7 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 
 // ------------------------------------------------------------------ border reset -----------
 // ref :544-551: everything outside isInBounds(resetBnd) -> 0
-__global__ void k_reset_border_vec4(float4 *__restrict__ vel, flof_dim4 d, int resetBnd)
+__global__ void k_reset_border_vec4(float4 *__restrict__ vel, flof_kd d, int resetBnd)
 {
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t)) return;
@@ -182,6 +189,8 @@ __global__ void k_reset_border_vec4(float4 *__restrict__ vel, flof_dim4 d, int r
 }
 int flof_reset_border_vec4(flof_ctx *ctx, float *vel, flof_dim4 d, int resetBnd)
 {
-	FLOF_LAUNCH(k_reset_border_vec4, flof_grid4(d), FLOF_BLOCK, 0, (float4 *)vel, d, resetBnd);
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
+	FLOF_LAUNCH(k_reset_border_vec4, g, FLOF_BLOCK, 0, (float4 *)vel, kd, resetBnd);
 	return FLOF_OK;
 }

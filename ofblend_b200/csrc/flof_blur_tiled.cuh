@@ -90,7 +90,7 @@ __device__ __forceinline__ void wacc4(float4 &v, float w, const float4 &q)  // s
 }
 
 // thread -> (x, y0): consecutive threads = consecutive x; one y-patch of FLOF_TPY rows per thread
-__device__ __forceinline__ bool tiled_xy(flof_dim4 d, int &x, int &y0)
+__device__ __forceinline__ bool tiled_xy(const flof_dim4 &d, int &x, int &y0)
 {
 	const int pty = (d.ny + FLOF_TPY - 1) / FLOF_TPY;
 	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
@@ -100,10 +100,12 @@ __device__ __forceinline__ bool tiled_xy(flof_dim4 d, int &x, int &y0)
 	y0 = py * FLOF_TPY;
 	return true;
 }
-static inline dim3 tiled_grid(flof_dim4 d)
+static inline flof_kd tiled_grid(const flof_ctx *ctx, flof_dim4 d, dim3 *g)
 {
+	const flof_kd kd = flof_kdim(ctx, d, g);  // z-dim = this rank's t-slices
 	const int pty = (d.ny + FLOF_TPY - 1) / FLOF_TPY;
-	return dim3((unsigned)(((int64_t)d.nx * pty + FLOF_BLOCK - 1) / FLOF_BLOCK), (unsigned)d.nz, (unsigned)d.nt);
+	g->x = (unsigned)(((int64_t)d.nx * pty + FLOF_BLOCK - 1) / FLOF_BLOCK);
+	return kd;
 }
 
 // ------------------------------------------------------------------ 81-tap extrapolation ---
@@ -113,11 +115,11 @@ static inline dim3 tiled_grid(flof_dim4 d)
 // the arithmetic and only copy.
 __global__ void __launch_bounds__(FLOF_BLOCK, 2)
     k_cv_expol_blur4d_tiled(const float4 *__restrict__ a, float4 *__restrict__ tmp, const float *__restrict__ mark,
-                            flof_dim4 d)
+                            flof_kd d)
 {
 	int x, y0;
 	if (!tiled_xy(d, x, y0)) return;
-	const int k = (int)blockIdx.y, t = (int)blockIdx.z;
+	const int k = (int)blockIdx.y, t = (int)blockIdx.z + d.t0;
 	const bool col_in = k >= 1 && k < d.nz - 1 && t >= 1 && t < d.nt - 1 && x >= 1 && x < d.nx - 1;
 	const int64_t plane = flof_idx(d, 0, 0, k, t);
 	bool need[FLOF_TPY];
@@ -179,7 +181,9 @@ __global__ void __launch_bounds__(FLOF_BLOCK, 2)
 
 int flof_launch_expol_tiled(flof_ctx *ctx, const float *a, float *tmp, const float *marker, flof_dim4 d)
 {
-	FLOF_LAUNCH(k_cv_expol_blur4d_tiled, tiled_grid(d), FLOF_BLOCK, 0, (const float4 *)a, (float4 *)tmp, marker, d);
+	dim3 g;
+	const flof_kd kd = tiled_grid(ctx, d, &g);
+	FLOF_LAUNCH(k_cv_expol_blur4d_tiled, g, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)tmp, marker, kd);
 	return FLOF_OK;
 }
 
@@ -197,12 +201,12 @@ template <int S> __device__ __forceinline__ int clip_state(int i, int n)
 // interior columns next to the x border are done by k_gauss_blur4d_cols (generic arithmetic).
 template <int S>
 __global__ void __launch_bounds__(FLOF_BLOCK, 3)
-    k_gauss_blur4d_tiled(const float4 *__restrict__ a, float4 *__restrict__ tmp, flof_dim4 d)
+    k_gauss_blur4d_tiled(const float4 *__restrict__ a, float4 *__restrict__ tmp, flof_kd d)
 {
 	constexpr int NS = 2 * S + 1;
 	int x, y0;
 	if (!tiled_xy(d, x, y0)) return;
-	const int k = (int)blockIdx.y, t = (int)blockIdx.z;
+	const int k = (int)blockIdx.y, t = (int)blockIdx.z + d.t0;
 	if (k < 1 || k >= d.nz - 1 || t < 1 || t >= d.nt - 1) return;  // KERNEL(fourd, bnd = 1)
 	if (x < S || x >= d.nx - S) return;                            // x-border columns: other kernel
 	p4 acc[FLOF_TPY];
@@ -261,14 +265,14 @@ __global__ void __launch_bounds__(FLOF_BLOCK, 3)
 // One thread per cell, the generic tap loop of flof_blur.cu.
 template <int S>
 __global__ void __launch_bounds__(FLOF_BLOCK)
-    k_gauss_blur4d_cols(const float4 *__restrict__ a, float4 *__restrict__ tmp, flof_dim4 d)
+    k_gauss_blur4d_cols(const float4 *__restrict__ a, float4 *__restrict__ tmp, flof_kd d)
 {
 	constexpr int NC = 2 * (S - 1);
 	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
 	if (NC == 0 || p >= (unsigned)(NC * d.ny)) return;
 	const int j = (int)(p / (unsigned)NC), ci = (int)(p - (unsigned)j * NC);
 	const int i = ci < S - 1 ? 1 + ci : d.nx - S + (ci - (S - 1));
-	const int k = (int)blockIdx.y, t = (int)blockIdx.z;
+	const int k = (int)blockIdx.y, t = (int)blockIdx.z + d.t0;
 	if (!flof_in_bounds(d, i, j, k, t, 1)) return;
 	float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
 	float weight = 0.f;
@@ -337,17 +341,19 @@ int flof_launch_gauss_tiled(flof_ctx *ctx, const float *a, float *tmp, flof_dim4
 		                            ctx->stream) != cudaSuccess)
 			return flof_fail(ctx, FLOF_ERR_CUDA, "gaussianBlur: weight table upload failed"), -1;
 	}
+	dim3 tg;
+	const flof_kd kd = tiled_grid(ctx, d, &tg);
 	const int pi = flof_prof_pre(ctx, s == 1 ? "k_gauss_blur4d_tiled<1>" : "k_gauss_blur4d_tiled<2>");
 	if (s == 1)
-		k_gauss_blur4d_tiled<1><<<tiled_grid(d), FLOF_BLOCK, 0, ctx->stream>>>((const float4 *)a, (float4 *)tmp, d);
+		k_gauss_blur4d_tiled<1><<<tg, FLOF_BLOCK, 0, ctx->stream>>>((const float4 *)a, (float4 *)tmp, kd);
 	else
-		k_gauss_blur4d_tiled<2><<<tiled_grid(d), FLOF_BLOCK, 0, ctx->stream>>>((const float4 *)a, (float4 *)tmp, d);
+		k_gauss_blur4d_tiled<2><<<tg, FLOF_BLOCK, 0, ctx->stream>>>((const float4 *)a, (float4 *)tmp, kd);
 	flof_prof_post(ctx, pi);
 	ctx->launches++;
 	if (s == 2) {
 		const int pj = flof_prof_pre(ctx, "k_gauss_blur4d_cols<2>");
-		dim3 g((unsigned)((2 * d.ny + FLOF_BLOCK - 1) / FLOF_BLOCK), (unsigned)d.nz, (unsigned)d.nt);
-		k_gauss_blur4d_cols<2><<<g, FLOF_BLOCK, 0, ctx->stream>>>((const float4 *)a, (float4 *)tmp, d);
+		dim3 g((unsigned)((2 * d.ny + FLOF_BLOCK - 1) / FLOF_BLOCK), (unsigned)d.nz, tg.z);
+		k_gauss_blur4d_cols<2><<<g, FLOF_BLOCK, 0, ctx->stream>>>((const float4 *)a, (float4 *)tmp, kd);
 		flof_prof_post(ctx, pj);
 		ctx->launches++;
 	}

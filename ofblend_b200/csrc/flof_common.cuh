@@ -59,7 +59,51 @@ struct flof_ctx {
 	const char **prof_name;
 	int64_t *prof_cells_of;  // per launch: cells of the grid level being processed
 	int64_t prof_cells;      // set by the multi-scale driver at each pyramid level
+	// multi-GPU: one context per rank, NCCL communicator over NVLink (flof_comm.cu)
+	void *comm;              // ncclComm_t
+	int rank, nranks;
+	int64_t shard_min_cells; // smaller pyramid levels are computed replicated on every rank
+	// t-sharding of the pyramid level currently being processed (set by the multi-scale driver):
+	// every rank keeps full-size grids in a global index space but computes and owns only the
+	// t-slices [ta, tb); ghost slices are refreshed by NCCL send/recv where a stencil needs them.
+	struct {
+		int active;
+		int nt;       // T of the sharded level: only grids with this T are sliced
+		int64_t n3;   // nx*ny*nz of the level
+		int ta, tb;
+	} sh;
 };
+
+// slab of this rank for a grid with `nt` slices: [0, nt) unless the grid belongs to the sharded level
+static inline void flof_slab(const flof_ctx *ctx, int nt, int *ta, int *tb)
+{
+	if (ctx->sh.active && nt == ctx->sh.nt) {
+		*ta = ctx->sh.ta;
+		*tb = ctx->sh.tb;
+	} else {
+		*ta = 0;
+		*tb = nt;
+	}
+}
+// same for flat kernels addressed by cell count
+static inline void flof_flat_range(const flof_ctx *ctx, int64_t cells, int64_t *c0, int64_t *c1)
+{
+	if (ctx->sh.active && cells == ctx->sh.n3 * ctx->sh.nt) {
+		*c0 = ctx->sh.n3 * ctx->sh.ta;
+		*c1 = ctx->sh.n3 * ctx->sh.tb;
+	} else {
+		*c0 = 0;
+		*c1 = cells;
+	}
+}
+static inline bool flof_sharded(const flof_ctx *ctx, int nt) { return ctx->sh.active && nt == ctx->sh.nt; }
+
+// communication helpers (flof_comm.cu); all are no-ops when the grid is not sharded
+int flof_halo_exchange(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes, int h);
+int flof_allgather_slabs(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes);
+int flof_allreduce_f64_sum(flof_ctx *ctx, double *dev, int n);
+int flof_allreduce_f32_max(flof_ctx *ctx, float *dev, int n);
+int flof_allreduce_f32_min(flof_ctx *ctx, float *dev, int n);
 
 static inline int flof_prof_pre(flof_ctx *ctx, const char *name)
 {
@@ -122,6 +166,20 @@ static inline dim3 flof_grid4(flof_dim4 d)
 	return dim3((unsigned)(((int64_t)d.nx * d.ny + FLOF_BLOCK - 1) / FLOF_BLOCK), (unsigned)d.nz,
 	            (unsigned)d.nt);
 }
+// kernel-side dims of a (possibly sliced) launch: global sizes + the first t-slice this launch covers
+struct flof_kd : flof_dim4 {
+	int t0;
+};
+static inline flof_kd flof_kdim(const flof_ctx *ctx, flof_dim4 d, dim3 *grid)
+{
+	int ta, tb;
+	flof_slab(ctx, d.nt, &ta, &tb);
+	flof_kd k;
+	k.nx = d.nx; k.ny = d.ny; k.nz = d.nz; k.nt = d.nt;
+	k.t0 = ta;
+	*grid = dim3((unsigned)(((int64_t)d.nx * d.ny + FLOF_BLOCK - 1) / FLOF_BLOCK), (unsigned)d.nz, (unsigned)(tb - ta));
+	return k;
+}
 static inline dim3 flof_grid3(flof_dim3 d)
 {
 	return dim3((unsigned)(((int64_t)d.nx * d.ny + FLOF_BLOCK - 1) / FLOF_BLOCK), (unsigned)d.nz, 1);
@@ -146,6 +204,16 @@ __device__ __forceinline__ bool flof_cell_ijkt(flof_dim4 d, int &i, int &j, int 
 	i = (int)(p - (unsigned)j * (unsigned)d.nx);
 	k = (int)blockIdx.y;
 	t = (int)blockIdx.z;
+	return true;
+}
+__device__ __forceinline__ bool flof_cell_ijkt(const flof_kd &d, int &i, int &j, int &k, int &t)
+{
+	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
+	if (p >= (unsigned)(d.nx * d.ny)) return false;
+	j = (int)(p / (unsigned)d.nx);
+	i = (int)(p - (unsigned)j * (unsigned)d.nx);
+	k = (int)blockIdx.y;
+	t = (int)blockIdx.z + d.t0;
 	return true;
 }
 __device__ __forceinline__ int64_t flof_idx(flof_dim4 d, int i, int j, int k, int t)

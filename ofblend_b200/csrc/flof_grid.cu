@@ -96,7 +96,11 @@ extern "C" int flof_grid_binary(flof_ctx *ctx, float *a, const float *b, int64_t
 {
 	FLOF_RET(check_elem(ctx, elem, a));
 	FLOF_RET(check_elem(ctx, elem, b));
-	const int64_t n = cells * elem;
+	int64_t c0, c1;
+	flof_flat_range(ctx, cells, &c0, &c1);  // t-slab of this rank if the grid belongs to the sharded level
+	a += c0 * elem;
+	b += c0 * elem;
+	const int64_t n = (c1 - c0) * elem;
 	const int blocks = flof_flat_blocks(ctx, (n + 3) / 4, 8);
 	switch (op) {
 	case FLOF_OP_ADD: FLOF_LAUNCH(k_binary<FLOF_OP_ADD>, blocks, FLOF_BLOCK, 0, a, b, n); break;
@@ -112,7 +116,11 @@ template <int UN>
 static int unary(flof_ctx *ctx, float *a, const float *b, int64_t cells, int elem, float4 f)
 {
 	FLOF_RET(check_elem(ctx, elem, a));
-	const int64_t n = cells * elem;
+	int64_t c0, c1;
+	flof_flat_range(ctx, cells, &c0, &c1);
+	a += c0 * elem;
+	if (b) b += c0 * elem;
+	const int64_t n = (c1 - c0) * elem;
 	const int blocks = flof_flat_blocks(ctx, (n + 3) / 4, 8);
 	if (elem == 4)
 		FLOF_LAUNCH((k_unary<UN, true>), blocks, FLOF_BLOCK, 0, a, b, n, f);
@@ -196,11 +204,17 @@ __global__ void k_min_max(const float *__restrict__ a, int64_t cells, flof_reduc
 // device-side min/max left in ctx->red->out_f[0..1]; no sync (used by advectCfl / corrVels)
 int flof_min_max_device(flof_ctx *ctx, const float *a, int64_t cells, int elem)
 {
-	const int blocks = flof_flat_blocks(ctx, cells, 8);
+	int64_t c0, c1;
+	flof_flat_range(ctx, cells, &c0, &c1);
+	const int blocks = flof_flat_blocks(ctx, c1 - c0, 8);
 	if (elem == 4)
-		FLOF_LAUNCH(k_min_max<4>, blocks, FLOF_BLOCK, 0, a, cells, ctx->red);
+		FLOF_LAUNCH(k_min_max<4>, blocks, FLOF_BLOCK, 0, a + c0 * 4, c1 - c0, ctx->red);
 	else
-		FLOF_LAUNCH(k_min_max<1>, blocks, FLOF_BLOCK, 0, a, cells, ctx->red);
+		FLOF_LAUNCH(k_min_max<1>, blocks, FLOF_BLOCK, 0, a + c0, c1 - c0, ctx->red);
+	if (c1 - c0 != cells) {  // sharded level: combine the slabs
+		FLOF_RET(flof_allreduce_f32_min(ctx, &ctx->red->out_f[0], 1));
+		FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->red->out_f[1], 1));
+	}
 	return FLOF_OK;
 }
 
@@ -331,7 +345,7 @@ extern "C" int flof_debug_grid_avg4d(flof_ctx *ctx, const float *phi, flof_dim4 
 
 // ------------------------------------------------------------------ boundaries ------------
 // ref: knSetBnd4d grid4d.cpp:355-363 (`<= w`: w+1 shells)
-template <class T> __global__ void k_set_bound4d(T *__restrict__ a, flof_dim4 d, T v, int w)
+template <class T> __global__ void k_set_bound4d(T *__restrict__ a, flof_kd d, T v, int w)
 {
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t)) return;
@@ -343,22 +357,25 @@ extern "C" int flof_grid4d_set_bound(flof_ctx *ctx, float *a, flof_dim4 d, int e
                                      const float v[4], int w)
 {
 	FLOF_ARG(elem == 1 || elem == 4, "flof_grid4d_set_bound: elem must be 1 or 4");
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
 	if (elem == 4)
-		FLOF_LAUNCH(k_set_bound4d<float4>, flof_grid4(d), FLOF_BLOCK, 0, (float4 *)a, d,
-		            make_float4(v[0], v[1], v[2], v[3]), w);
+		FLOF_LAUNCH(k_set_bound4d<float4>, g, FLOF_BLOCK, 0, (float4 *)a, kd, make_float4(v[0], v[1], v[2], v[3]), w);
 	else
-		FLOF_LAUNCH(k_set_bound4d<float>, flof_grid4(d), FLOF_BLOCK, 0, a, d, v[0], w);
+		FLOF_LAUNCH(k_set_bound4d<float>, g, FLOF_BLOCK, 0, a, kd, v[0], w);
 	return FLOF_OK;
 }
 extern "C" int flof_grid4d_set_bound_int(flof_ctx *ctx, int *a, flof_dim4 d, int v, int w)
 {
-	FLOF_LAUNCH(k_set_bound4d<int>, flof_grid4(d), FLOF_BLOCK, 0, a, d, v, w);
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
+	FLOF_LAUNCH(k_set_bound4d<int>, g, FLOF_BLOCK, 0, a, kd, v, w);
 	return FLOF_OK;
 }
 
 // ref: knSetBnd4dNeumann grid4d.cpp:370-407.  Source cells are never boundary cells
 // themselves (for sizes > 2w+3), so the in-place update is race-free.
-template <class T> __global__ void k_set_bound_neumann4d(T *a, flof_dim4 d, int w)
+template <class T> __global__ void k_set_bound_neumann4d(T *a, flof_kd d, int w)
 {
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t)) return;
@@ -379,10 +396,14 @@ extern "C" int flof_grid4d_set_bound_neumann(flof_ctx *ctx, float *a, flof_dim4 
 	FLOF_ARG(elem == 1 || elem == 4, "flof_grid4d_set_bound_neumann: elem must be 1 or 4");
 	FLOF_ARG(d.nx > 2 * w + 3 && d.ny > 2 * w + 3 && d.nz > 2 * w + 3 && d.nt > 2 * w + 3,
 	         "flof_grid4d_set_bound_neumann: grid too small for width %d", w);
+	// sharded: the source slice of a t-border cell (w+1 / nt-2-w) must lie in the same slab
+	if (flof_sharded(ctx, d.nt)) FLOF_ARG(ctx->sh.tb - ctx->sh.ta >= w + 2, "setBoundNeumann: slab thinner than the boundary width");
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
 	if (elem == 4)
-		FLOF_LAUNCH(k_set_bound_neumann4d<float4>, flof_grid4(d), FLOF_BLOCK, 0, (float4 *)a, d, w);
+		FLOF_LAUNCH(k_set_bound_neumann4d<float4>, g, FLOF_BLOCK, 0, (float4 *)a, kd, w);
 	else
-		FLOF_LAUNCH(k_set_bound_neumann4d<float>, flof_grid4(d), FLOF_BLOCK, 0, a, d, w);
+		FLOF_LAUNCH(k_set_bound_neumann4d<float>, g, FLOF_BLOCK, 0, a, kd, w);
 	return FLOF_OK;
 }
 
@@ -538,7 +559,7 @@ extern "C" void flof_grid_factor4d(const float s1[4], const float s2in[4], const
 // One thread per target cell; gathers hit L1/L2 (down-sampling reads each source cell once,
 // up-sampling re-reads a 16x smaller source).
 template <class T>
-__global__ void k_interpol4d(T *__restrict__ dst, flof_dim4 td, const T *__restrict__ src,
+__global__ void k_interpol4d(T *__restrict__ dst, flof_kd td, const T *__restrict__ src,
                              flof_dim4 sd, float4 fac, float4 off)
 {
 	int i, j, k, t;
@@ -554,11 +575,12 @@ extern "C" int flof_kn_interpol4d(flof_ctx *ctx, float *dst, flof_dim4 td, const
 	FLOF_ARG(sd.nx >= 2 && sd.ny >= 2 && sd.nz >= 2 && sd.nt >= 2, "interpolation source too small");
 	const float4 f = make_float4(srcFac[0], srcFac[1], srcFac[2], srcFac[3]);
 	const float4 o = make_float4(off[0], off[1], off[2], off[3]);
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, td, &g);  // sharded target: only this rank's slices (source must be complete)
 	if (elem == 4)
-		FLOF_LAUNCH(k_interpol4d<float4>, flof_grid4(td), FLOF_BLOCK, 0, (float4 *)dst, td,
-		            (const float4 *)src, sd, f, o);
+		FLOF_LAUNCH(k_interpol4d<float4>, g, FLOF_BLOCK, 0, (float4 *)dst, kd, (const float4 *)src, sd, f, o);
 	else
-		FLOF_LAUNCH(k_interpol4d<float>, flof_grid4(td), FLOF_BLOCK, 0, dst, td, src, sd, f, o);
+		FLOF_LAUNCH(k_interpol4d<float>, g, FLOF_BLOCK, 0, dst, kd, src, sd, f, o);
 	return FLOF_OK;
 }
 extern "C" int flof_interpolate_grid4d(flof_ctx *ctx, float *dst, flof_dim4 td, const float *src,

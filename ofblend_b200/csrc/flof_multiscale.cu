@@ -11,6 +11,8 @@
 #include "flof_common.cuh"
 
 extern float g_flof_last_cg_ms;
+int flof_advect_cfl4d_ex(flof_ctx *ctx, float cfl, const float *vel, float *grid, flof_dim4 d, int elem,
+                         float velFactor, int grid_complete);
 int flof_optical_flow4d_ex(flof_ctx *ctx, float *vel, const float *i0, const float *i1, float *rhsT, flof_dim4 d,
                             float wSmooth, float wEnergy, float postVelBlur, float cgAccuracy,
                             float resetBndWidth, int vel_is_zero, int *cgIters, float *cgRes);
@@ -22,12 +24,11 @@ int flof_optical_flow4d_ex(flof_ctx *ctx, float *vel, const float *i0, const flo
 template <bool SMOKE>
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_ls_diff_rows(const float *__restrict__ i0, const float *__restrict__ i1, float *__restrict__ out,
-                   flof_dim4 d, float correction, int bnd, flof_reduce_scratch *red)
+                   flof_dim4 d, float correction, int bnd, int row0, int row1, flof_reduce_scratch *red)
 {
 	__shared__ double sh[32];
 	double acc = 0.;
-	const int rows = d.ny * d.nz * d.nt;  // one row = nx cells
-	for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+	for (int row = row0 + blockIdx.x; row < row1; row += gridDim.x) {  // one row = nx cells
 		const int j = row % d.ny, k = (row / d.ny) % d.nz, t = row / (d.ny * d.nz);
 		for (int i = threadIdx.x; i < d.nx; i += blockDim.x) {
 			if (!flof_in_bounds(d, i, j, k, t, bnd)) continue;
@@ -59,12 +60,16 @@ template <bool SMOKE>
 static int ls_diff(flof_ctx *ctx, const float *i0, const float *i1, float *out, flof_dim4 d, float correction,
                    int bnd, float *result)
 {
-	const int64_t rows = (int64_t)d.ny * d.nz * d.nt;
+	int ta, tb;
+	flof_slab(ctx, d.nt, &ta, &tb);  // sharded level: sum this rank's slices, then all-reduce
+	const int row0 = ta * d.ny * d.nz, row1 = tb * d.ny * d.nz;
+	const int64_t rows = row1 - row0;
 	int blocks = ctx->sm_count * 8;
 	if (blocks > FLOF_MAX_PARTIALS) blocks = FLOF_MAX_PARTIALS;
 	if (blocks > rows) blocks = (int)rows;
 	const int threads = d.nx >= 128 ? 128 : (d.nx > 32 ? 64 : 32);
-	FLOF_LAUNCH(k_ls_diff_rows<SMOKE>, blocks, threads, 0, i0, i1, out, d, correction, bnd, ctx->red);
+	FLOF_LAUNCH(k_ls_diff_rows<SMOKE>, blocks, threads, 0, i0, i1, out, d, correction, bnd, row0, row1, ctx->red);
+	if (tb - ta != d.nt) FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->red->out_d[2], 1));
 	double *h = (double *)ctx->pinned;
 	FLOF_CK(cudaMemcpyAsync(h, &ctx->red->out_d[2], sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	FLOF_CK(cudaStreamSynchronize(ctx->stream));
@@ -137,10 +142,31 @@ void tr_err(flof_multiscale_trace *tr, float e)
 		if (r__ != FLOF_OK) return r__;    \
 	} while (0)
 
-int advect_cfl(flof_ctx *ctx, float cfl, const float *vel, float *grid, flof_dim4 d, int elem)
+// complete: `grid` is valid on all slices (fresh copy of an input) -> no all-gather on a sharded level
+int advect_cfl(flof_ctx *ctx, float cfl, const float *vel, float *grid, flof_dim4 d, int elem, int complete)
 {
-	return flof_advect_cfl4d(ctx, cfl, vel, grid, d, elem, 1.f);
+	return flof_advect_cfl4d_ex(ctx, cfl, vel, grid, d, elem, 1.f, complete);
 }
+
+// RAII: shard the level being processed along t over the ranks, restore the caller's state on exit
+struct ShardScope {
+	flof_ctx *ctx;
+	decltype(flof_ctx::sh) saved;
+	ShardScope(flof_ctx *c, flof_dim4 d) : ctx(c), saved(c->sh)
+	{
+		const int64_t n = flof_cells(d);
+		const int P = ctx->nranks;
+		const bool ok = ctx->comm && P > 1 && d.nt % P == 0 && d.nt / P >= 4 && n >= ctx->shard_min_cells;
+		ctx->sh.active = ok ? 1 : 0;
+		if (ok) {
+			ctx->sh.nt = d.nt;
+			ctx->sh.n3 = (int64_t)d.nx * d.ny * d.nz;
+			flof_slab_range(d.nt, P, ctx->rank, &ctx->sh.ta, &ctx->sh.tb);
+		}
+	}
+	void reapply() {}
+	~ShardScope() { ctx->sh = saved; }
+};
 
 // ref opticalFlowMultiscaleTemplate :936-1173
 int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof_dim4 d,
@@ -154,6 +180,11 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 	const float projMaxIter = 40.f;
 	const float lsDiffFac = (float)(0.1 / 20.);
 	ctx->prof_cells = n;  // tag launches with the level they work on (flof_profile_*)
+	// Multi-GPU: on entry vel, i0, i1 are complete on every rank.  If this level is sharded, every
+	// operator below works on this rank's t-slab (ghost slices / all-gathers where a stencil or a
+	// gather needs them); vel is all-gathered before returning so the contract holds for the caller.
+	// Levels that are too small (or whose T is not divisible) run replicated on every rank.
+	const size_t vslice = sizeof(float) * 4 * (size_t)d.nx * d.ny * d.nz;
 
 	DevBuf i0warped(ctx);
 	MS_RET(i0warped.alloc(rb, false));
@@ -163,6 +194,8 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 	(void)errPreOf;
 
 	if (d.nx > P.minGridSize) {
+		// the coarser level decides about its own sharding; down-sampling runs on complete inputs
+		ShardScope none(ctx, flof_dim4{ 0, 0, 0, 0 });
 		flof_dim4 s = { d.nx / 2, d.ny / 2, d.nz / 2, d.nt / 2 };
 		if (s.nx < 3 || s.ny < 3 || s.nz < 3 || s.nt < 3)
 			return flof_fail(ctx, FLOF_ERR_ARG, "opticalFlowMultiscale4d: coarse level %dx%dx%dx%d too small",
@@ -180,13 +213,14 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 		float eSm = 0.f;
 		MS_RET(multiscale(ctx, velSm.f(), i0Sm.f(), i1Sm.f(), s, P, level + 1, multiStep, doFinalProject, tr, &eSm));
 		ctx->prof_cells = n;
-		MS_RET(flof_interpol_grid_templ(ctx, vel, d, velSm.f(), s, 4));
+		MS_RET(flof_interpol_grid_templ(ctx, vel, d, velSm.f(), s, 4));  // complete (cheap), sliced below
 		const float two[4] = { 2.f, 2.f, 2.f, 2.f };
 		MS_RET(flof_grid_mult_const(ctx, vel, n, 4, two));
 	}
+	ShardScope shard(ctx, d);
 
 	// pre-warp (ref :1011-1018)
-	MS_RET(advect_cfl(ctx, P.cfl, vel, i0warped.f(), d, 1));
+	MS_RET(advect_cfl(ctx, P.cfl, vel, i0warped.f(), d, 1, 1));
 	MS_RET(flof_grid4d_set_bound_neumann(ctx, i0warped.f(), d, 1, 0));
 	float errCurr = 0.f;
 	MS_RET(flof_calc_ls_diff4d(ctx, i0warped.f(), i1, NULL, d, lsDiffFac, resetBnd, &errCurr));
@@ -238,11 +272,11 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 			if (velBlur < 2.f) velBlur = 2.f;
 			for (int k = of; k >= 0; --k) MS_RET(flof_memcpy_d2d(ctx, vs2[k]->p, vs[k]->p, vb));
 			for (int k = of - 1; k >= 0; --k)
-				for (int l = 0; l < k; ++l) MS_RET(advect_cfl(ctx, P.cfl, vs2[k]->f(), vs2[l]->f(), d, 4));
+				for (int l = 0; l < k; ++l) MS_RET(advect_cfl(ctx, P.cfl, vs2[k]->f(), vs2[l]->f(), d, 4, 0));
 			MS_RET(flof_memcpy_d2d(ctx, tmpVel.p, vel, vb));
 			for (int k = of; k >= 0; --k) MS_RET(flof_grid_binary(ctx, tmpVel.f(), vs2[k]->f(), n, 4, FLOF_OP_ADD));
 			MS_RET(flof_memcpy_d2d(ctx, i0warp2.p, i0, rb));
-			MS_RET(advect_cfl(ctx, P.cfl, tmpVel.f(), i0warp2.f(), d, 1));
+			MS_RET(advect_cfl(ctx, P.cfl, tmpVel.f(), i0warp2.f(), d, 1, 1));
 			MS_RET(flof_grid4d_set_bound_neumann(ctx, i0warp2.f(), d, 1, 0));
 			float errC = 0.f;
 			MS_RET(flof_calc_ls_diff4d(ctx, i0warp2.f(), i1, NULL, d, lsDiffFac, resetBnd, &errC));
@@ -255,7 +289,7 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 			errLast = errC;
 		}
 		for (int of = ofStepsCurr - 1; of >= 0; --of)
-			for (int l = 0; l < of; ++l) MS_RET(advect_cfl(ctx, P.cfl, vs[of]->f(), vs[l]->f(), d, 4));
+			for (int l = 0; l < of; ++l) MS_RET(advect_cfl(ctx, P.cfl, vs[of]->f(), vs[l]->f(), d, 4, 0));
 		for (int of = 0; of < ofStepsCurr; ++of) MS_RET(flof_grid_binary(ctx, vel, vs[of]->f(), n, 4, FLOF_OP_ADD));
 	} else {
 		DevBuf velCurr(ctx);
@@ -291,13 +325,15 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 	// re-advect and evaluate on the finest level (ref :1155-1170)
 	if (level == 0) {
 		MS_RET(flof_memcpy_d2d(ctx, i0warped.p, i0, rb));
-		MS_RET(advect_cfl(ctx, P.cfl, vel, i0warped.f(), d, 1));
+		MS_RET(advect_cfl(ctx, P.cfl, vel, i0warped.f(), d, 1, 1));
 		MS_RET(flof_grid4d_set_bound_neumann(ctx, i0warped.f(), d, 1, 0));
 		float errFinal = 0.f;
 		MS_RET(flof_calc_ls_diff4d(ctx, i0warped.f(), i1, NULL, d, lsDiffFac, resetBnd, &errFinal));
 		errCurr = errFinal;
 		tr_err(tr, errFinal);
 	}
+	// leave the level with a complete deformation on every rank
+	MS_RET(flof_allgather_slabs(ctx, vel, d.nt, vslice));
 	*errOut = errCurr;
 	return FLOF_OK;
 }

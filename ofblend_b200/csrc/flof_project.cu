@@ -14,7 +14,7 @@ int flof_gaussian_blur4d_impl(flof_ctx *ctx, float *a, flof_dim4 d, int elem, fl
 
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_project_cells(float4 *__restrict__ dst, const float4 *__restrict__ vel, const float *__restrict__ phiOrg,
-                    const float *__restrict__ phiTarget, float *__restrict__ marker, flof_dim4 d,
+                    const float *__restrict__ phiTarget, float *__restrict__ marker, flof_kd d,
                     float threshPhi, int maxIter, float dt)
 {
 	int i, j, k, t;
@@ -83,8 +83,10 @@ extern "C" int flof_project_cells(flof_ctx *ctx, float *dst, const float *vel, c
                                   int maxIter)
 {
 	FLOF_ARG(d.nx >= 2 && d.ny >= 2 && d.nz >= 2 && d.nt >= 2, "corrVelsOf4d: grid too small");
-	FLOF_LAUNCH(k_project_cells, flof_grid4(d), FLOF_BLOCK, 0, (float4 *)dst, (const float4 *)vel, phiOrg,
-	            phiTarget, marker, d, threshPhi, maxIter, 1.0f);
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);  // sharded: phiOrg must be complete, everything else is per cell
+	FLOF_LAUNCH(k_project_cells, g, FLOF_BLOCK, 0, (float4 *)dst, (const float4 *)vel, phiOrg, phiTarget, marker, kd,
+	            threshPhi, maxIter, 1.0f);
 	return FLOF_OK;
 }
 

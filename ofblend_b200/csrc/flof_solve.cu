@@ -48,7 +48,7 @@ static flof_of_consts of_consts(float wSmooth, float wEnergy)
 // has_vel, the incoming vel with its clamped neighbours; writes grad and rhs (16 B each).
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_of_assemble(float4 *__restrict__ grad, float4 *__restrict__ rhs, const float *__restrict__ i0,
-                  const float *__restrict__ i1, const float4 *__restrict__ vel, flof_dim4 d,
+                  const float *__restrict__ i1, const float4 *__restrict__ vel, flof_kd d,
                   float wSmooth, float wEnergy, float mDx, float dxf, int has_vel)
 {
 	int i, j, k, t;
@@ -105,8 +105,10 @@ extern "C" int flof_of_assemble(flof_ctx *ctx, float *grad, float *rhs, const fl
 	FLOF_ARG(d.nx >= 3 && d.ny >= 3 && d.nz >= 3 && d.nt >= 3, "opticalFlow4d: grid too small");
 	const float mDx = (float)(1. / d.nx);           // ref :369
 	const float dxf = (float)(1. / (2. * mDx));     // ref :441
-	FLOF_LAUNCH(k_of_assemble, flof_grid4(d), FLOF_BLOCK, 0, (float4 *)grad, (float4 *)rhs, i0, i1,
-	            (const float4 *)vel, d, wSmooth, wEnergy, mDx, dxf, vel != NULL);
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);  // sharded: i1 (and vel) must be valid on the +-1 ghost slices
+	FLOF_LAUNCH(k_of_assemble, g, FLOF_BLOCK, 0, (float4 *)grad, (float4 *)rhs, i0, i1, (const float4 *)vel, kd, wSmooth,
+	            wEnergy, mDx, dxf, vel != NULL);
 	return FLOF_OK;
 }
 
@@ -133,11 +135,36 @@ __device__ __forceinline__ float axpy1(float a, double b, float c)
 	return (float)((double)a + b * (double)c);
 }
 
+// state after the initial residual / sigma are known (ref :286-301)
+__device__ __forceinline__ void cg_init_finalize(flof_cg_state *st, double s, float m, float accuracy)
+{
+	const double residual = (double)m;  // ref :286
+	st->iter = 0;
+	st->done = 0;
+	st->status = 0;
+	st->residual = m;
+	st->relResidual = 1e10f;  // cgRes initial value, ref :499
+	st->resIni = residual;
+	st->acc = (double)accuracy * residual;  // ref :292
+	st->sigma[0] = s;
+	st->sigma[1] = s;
+	st->alpha1 = 0.;
+	st->sigmaNew = 0.;
+	if (residual < (double)FLOF_VECTOR_EPSILON) {  // ref :287-291
+		st->done = 1;
+		st->status = 2;
+		st->relResidual = 0.f;
+	} else if (s == 0. || s != s) {  // ref :298-301
+		st->done = 1;
+		st->status = 3;
+	}
+}
+
 // res = rhs, result = 0, tmp = res*precond, srch = tmp; residual0 = max(res), sigma = tmp.res
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_cg_init(float4 *__restrict__ x, float4 *__restrict__ res, float4 *__restrict__ srch,
               const float4 *__restrict__ grad, const float4 *__restrict__ rhs, int64_t cells, float diag,
-              float accuracy, flof_reduce_scratch *red, flof_cg_state *st)
+              float accuracy, int multi, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	__shared__ double shd[32];
 	__shared__ float shf[32];
@@ -170,28 +197,21 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		s = flof_block_sum(s, shd);
 		m = flof_block_max(m, shf);
 		if (threadIdx.x == 0) {
-			const double residual = (double)m;  // ref :286
-			st->iter = 0;
-			st->done = 0;
-			st->status = 0;
-			st->residual = m;
-			st->relResidual = 1e10f;  // cgRes initial value, ref :499
-			st->resIni = residual;
-			st->acc = (double)accuracy * residual;  // ref :292
-			st->sigma[0] = s;
-			st->sigma[1] = s;
-			st->alpha1 = 0.;
-			st->sigmaNew = 0.;
-			if (residual < (double)FLOF_VECTOR_EPSILON) {  // ref :287-291
-				st->done = 1;
-				st->status = 2;
-				st->relResidual = 0.f;
-			} else if (s == 0. || s != s) {  // ref :298-301
-				st->done = 1;
-				st->status = 3;
+			if (multi) {  // raw slab results; the ranks are combined by NCCL, then k_cg_init_finalize runs
+				st->sigmaNew = s;
+				st->residual = m;
+				st->done = 0;
+			} else {
+				cg_init_finalize(st, s, m, accuracy);
 			}
 		}
 	}
+}
+__global__ void k_cg_init_finalize(float accuracy, flof_cg_state *st) { cg_init_finalize(st, st->sigmaNew, st->residual, accuracy); }
+__global__ void k_cg_update_finalize(flof_cg_state *st)
+{
+	if (st->done) return;
+	st->relResidual = (float)((double)st->residual / st->resIni);
 }
 
 // A: tmp = A * srch (ref applyMat :211-232), partial dot(srch, tmp)
@@ -357,10 +377,23 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 {
 	const int64_t cells = flof_cells(d);
 	const flof_of_consts k = of_consts(wSmooth, wEnergy);
-	const int blocks = flof_flat_blocks(ctx, cells, 8);
 	const int64_t sY = d.nx, sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
-	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, (float4 *)x, (float4 *)res, (float4 *)srch,
-	            (const float4 *)grad, (const float4 *)rhs, cells, k.diag, accuracy, ctx->red, ctx->cg);
+	// sharded level: this rank iterates over its t-slab only; srch needs one ghost slice per side
+	// before every apply, the three scalars of an iteration are all-reduced over the ranks
+	int64_t c0, c1;
+	flof_flat_range(ctx, cells, &c0, &c1);
+	const int multi = (c1 - c0 != cells && ctx->nranks > 1) ? 1 : 0;
+	const int64_t n = c1 - c0;
+	const int blocks = flof_flat_blocks(ctx, n, 8);
+	float4 *X = (float4 *)x + c0, *R = (float4 *)res + c0, *P = (float4 *)srch + c0, *AP = (float4 *)tmp + c0;
+	const float4 *G = (const float4 *)grad + c0, *B = (const float4 *)rhs + c0;
+	const size_t slice_bytes = sizeof(float4) * (size_t)sT;
+	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, X, R, P, G, B, n, k.diag, accuracy, multi, ctx->red, ctx->cg);
+	if (multi) {
+		FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
+		FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));
+		FLOF_LAUNCH(k_cg_init_finalize, 1, 1, 0, accuracy, ctx->cg);
+	}
 	flof_cg_state *h = (flof_cg_state *)ctx->pinned;
 	int launched = 0;
 	// poll the device-side done flag every `chunk` iterations; iterations after convergence are
@@ -371,12 +404,18 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 		FLOF_CK(cudaStreamSynchronize(ctx->stream));
 		if (h->done || launched >= maxIter) break;
 		for (int q = 0; q < chunk && launched < maxIter; ++q, ++launched) {
-			FLOF_LAUNCH(k_cg_apply, blocks, FLOF_BLOCK, 0, (float4 *)tmp, (const float4 *)srch,
-			            (const float4 *)grad, cells, sY, sZ, sT, k.offd, k.diag, ctx->red, ctx->cg);
-			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, (float4 *)x, (float4 *)res, (const float4 *)srch,
-			            (const float4 *)tmp, (const float4 *)grad, cells, k.diag, ctx->red, ctx->cg);
-			FLOF_LAUNCH(k_cg_direction, blocks, FLOF_BLOCK, 0, (float4 *)srch, (const float4 *)res,
-			            (const float4 *)grad, cells, k.diag, maxIter, ctx->cg);
+			if (multi) FLOF_RET(flof_halo_exchange(ctx, srch, d.nt, slice_bytes, 1));
+			FLOF_LAUNCH(k_cg_apply, blocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, n, sY, sZ, sT, k.offd, k.diag, ctx->red,
+			            ctx->cg);
+			if (multi) FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->alpha1, 1));
+			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, X, R, (const float4 *)P, (const float4 *)AP, G, n, k.diag, ctx->red,
+			            ctx->cg);
+			if (multi) {
+				FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
+				FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));
+				FLOF_LAUNCH(k_cg_update_finalize, 1, 1, 0, ctx->cg);
+			}
+			FLOF_LAUNCH(k_cg_direction, blocks, FLOF_BLOCK, 0, P, (const float4 *)R, G, n, k.diag, maxIter, ctx->cg);
 			FLOF_LAUNCH(k_cg_advance, 1, 1, 0, maxIter, ctx->cg);
 		}
 		if (launched >= 32) chunk = 16;
@@ -456,8 +495,10 @@ int flof_optical_flow4d_ex(flof_ctx *ctx, float *vel, const float *i0, const flo
 	}
 	if (rc == FLOF_OK) {
 		const float mDx = (float)(1. / d.nx);
-		FLOF_LAUNCH(k_of_copy_back, flof_flat_blocks(ctx, cells, 8), FLOF_BLOCK, 0, (float4 *)vel,
-		            (const float4 *)x, (const float4 *)rhs, rhsT, cells, mDx);
+		int64_t c0, c1;
+		flof_flat_range(ctx, cells, &c0, &c1);
+		FLOF_LAUNCH(k_of_copy_back, flof_flat_blocks(ctx, c1 - c0, 8), FLOF_BLOCK, 0, (float4 *)vel + c0,
+		            (const float4 *)x + c0, (const float4 *)rhs + c0, rhsT ? rhsT + c0 : NULL, c1 - c0, mDx);
 	}
 	flof_tmp_free(ctx, grad);
 	flof_tmp_free(ctx, rhs);
