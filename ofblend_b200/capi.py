@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflof_b200.so")
+LIB_PATH = os.environ.get("FLOF_B200_LIB") or os.path.join(_HERE, "libflof_b200.so")  # env override: A/B builds
 
 
 class Dim4(C.Structure):

@@ -109,53 +109,74 @@ static inline flof_kd tiled_grid(const flof_ctx *ctx, flof_dim4 d, dim3 *g)
 }
 
 // ------------------------------------------------------------------ 81-tap extrapolation ---
-// Per (vt, zk) pair the thread loads its FLOF_TPY+2 rows x 3 columns (18 independent LDG.128 in
+#ifndef FLOF_ETPY
+#define FLOF_ETPY 4  // outputs per thread along y
+#define FLOF_EBLK 2  // resident CTAs per SM the register budget is tuned for
+#endif
+#ifndef FLOF_EZCH
+#define FLOF_EZCH 16  // z-planes walked by one CTA
+#endif
+template <int TPY> __device__ __forceinline__ bool tiled_xy_n(const flof_dim4 &d, int &x, int &y0)
+{
+	const int pty = (d.ny + TPY - 1) / TPY;
+	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
+	if (p >= (unsigned)(d.nx * pty)) return false;
+	const int py = (int)(p / (unsigned)d.nx);
+	x = (int)(p - (unsigned)py * (unsigned)d.nx);
+	y0 = py * TPY;
+	return true;
+}
+// Per (vt, zk) pair the thread loads its FLOF_ETPY+2 rows x 3 columns (18 independent LDG.128 in
 // flight) and then issues the 9 adds of each of its 4 outputs; row addresses are 32-bit offsets
 // computed once per thread.  Lanes on the x border and patches whose cells are all marked skip
 // the arithmetic and only copy.
-__global__ void __launch_bounds__(FLOF_BLOCK, 2)
+__global__ void __launch_bounds__(FLOF_BLOCK, FLOF_EBLK)
     k_cv_expol_blur4d_tiled(const float4 *__restrict__ a, float4 *__restrict__ tmp, const float *__restrict__ mark,
                             flof_kd d)
 {
 	int x, y0;
-	if (!tiled_xy(d, x, y0)) return;
-	const int k = (int)blockIdx.y, t = (int)blockIdx.z + d.t0;
+	if (!tiled_xy_n<FLOF_ETPY>(d, x, y0)) return;
+	const int t = (int)blockIdx.z + d.t0;
+	// z-marching: a CTA walks FLOF_EZCH consecutive z-planes, so the rows of plane z+1 that it pulls from
+	// L2 for output plane z are still in L1 when it computes planes z+1 and z+2 (ncu: the one-plane-per-CTA
+	// version was L2->L1 bandwidth bound, every row being fetched by 9 different CTAs)
+	for (int k = (int)blockIdx.y * FLOF_EZCH, kend = min(k + FLOF_EZCH, d.nz); k < kend; ++k) {
 	const bool col_in = k >= 1 && k < d.nz - 1 && t >= 1 && t < d.nt - 1 && x >= 1 && x < d.nx - 1;
 	const int64_t plane = flof_idx(d, 0, 0, k, t);
-	bool need[FLOF_TPY];
+	bool need[FLOF_ETPY];
 	bool any = false;
 #pragma unroll
-	for (int oy = 0; oy < FLOF_TPY; ++oy) {
+	for (int oy = 0; oy < FLOF_ETPY; ++oy) {
 		const int y = y0 + oy;
 		bool n = col_in && y >= 1 && y < d.ny - 1;
 		if (n) n = __ldg(mark + plane + (int64_t)y * d.nx + x) == 0.f;
 		need[oy] = n;
 		any |= n;
 	}
-	p4 acc[FLOF_TPY];
+	p4 acc[FLOF_ETPY];
 #pragma unroll
-	for (int oy = 0; oy < FLOF_TPY; ++oy) acc[oy] = p4_zero();
+	for (int oy = 0; oy < FLOF_ETPY; ++oy) acc[oy] = p4_zero();
 	if (any) {  // col_in holds: x-1 and x+1 are inside the grid
-		int roff[FLOF_TPY + 2];  // offset of (x, clamp(y0-1+r)) inside a z-t plane
+		int roff[FLOF_ETPY + 2];  // offset of (x, clamp(y0-1+r)) inside a z-t plane
 #pragma unroll
-		for (int r = 0; r < FLOF_TPY + 2; ++r) roff[r] = min(max(y0 - 1 + r, 0), d.ny - 1) * d.nx + x;
+		for (int r = 0; r < FLOF_ETPY + 2; ++r) roff[r] = min(max(y0 - 1 + r, 0), d.ny - 1) * d.nx + x;
 		const int64_t sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
 		for (int vt = t - 1; vt <= t + 1; ++vt) {
 			const float4 *base = a + (sT * vt + sZ * (k - 1));
 #pragma unroll 1
 			for (int zk = 0; zk < 3; ++zk, base += sZ) {
-				p4 L[FLOF_TPY + 2][3];
+				p4 L[FLOF_ETPY + 2][3];
 #pragma unroll
-				for (int r = 0; r < FLOF_TPY + 2; ++r) {
+				for (int r = 0; r < FLOF_ETPY + 2; ++r) {
 					const float4 *row = base + roff[r];
 					L[r][0] = p4_load(row - 1);
 					L[r][1] = p4_load(row);
 					L[r][2] = p4_load(row + 1);
 				}
 #pragma unroll
-				for (int r = 0; r < FLOF_TPY + 2; ++r)
+				for (int r = 0; r < FLOF_ETPY + 2; ++r)
 #pragma unroll
-					for (int oy = 0; oy < FLOF_TPY; ++oy) {
+					for (int oy = 0; oy < FLOF_ETPY; ++oy) {
 						if (r < oy || r > oy + 2) continue;
 						acc4(acc[oy], L[r][0]);
 						acc4(acc[oy], L[r][1]);
@@ -166,7 +187,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK, 2)
 	}
 	const double f = 1. / 81.0;
 #pragma unroll
-	for (int oy = 0; oy < FLOF_TPY; ++oy) {
+	for (int oy = 0; oy < FLOF_ETPY; ++oy) {
 		const int y = y0 + oy;
 		if (y >= d.ny) continue;
 		const int64_t c = plane + (int64_t)y * d.nx + x;
@@ -177,12 +198,15 @@ __global__ void __launch_bounds__(FLOF_BLOCK, 2)
 			tmp[c] = __ldg(a + c);
 		}
 	}
+	}  // z-march
 }
 
 int flof_launch_expol_tiled(flof_ctx *ctx, const float *a, float *tmp, const float *marker, flof_dim4 d)
 {
 	dim3 g;
 	const flof_kd kd = tiled_grid(ctx, d, &g);
+	g.x = (unsigned)(((int64_t)d.nx * ((d.ny + FLOF_ETPY - 1) / FLOF_ETPY) + FLOF_BLOCK - 1) / FLOF_BLOCK);
+	g.y = (unsigned)((d.nz + FLOF_EZCH - 1) / FLOF_EZCH);
 	FLOF_LAUNCH(k_cv_expol_blur4d_tiled, g, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)tmp, marker, kd);
 	return FLOF_OK;
 }
