@@ -114,7 +114,7 @@ static inline flof_kd tiled_grid(const flof_ctx *ctx, flof_dim4 d, dim3 *g)
 #define FLOF_EBLK 2  // resident CTAs per SM the register budget is tuned for
 #endif
 #ifndef FLOF_EZCH
-#define FLOF_EZCH 16  // z-planes walked by one CTA
+#define FLOF_EZCH 8   // z-planes walked by one CTA
 #endif
 template <int TPY> __device__ __forceinline__ bool tiled_xy_n(const flof_dim4 &d, int &x, int &y0)
 {
