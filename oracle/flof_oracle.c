@@ -409,6 +409,17 @@ static double block_tree(const double *t) /* flof_block_sum for blockDim 256 */
 	for (int l = 0; l < 32; ++l) v[l] = l < 8 ? sh[l] : 0.0;
 	return warp_tree(v);
 }
+/* cell visited by work index w of k_cg_apply<TILED> (8 x 8 x 4 bricks), see flof_solve.cu cg_tile_cell */
+static int g_dot_tiled = 0;
+static orc_dim4 g_dot_dims;
+static i64 gpu_tile_cell(orc_dim4 d, i64 w)
+{
+	const unsigned ntx = d.nx / 8, nty = d.ny / 8, ntz = d.nz / 4;
+	const unsigned T = (unsigned)(w >> 8), tid = (unsigned)w & 255u;
+	const unsigned tx = T % ntx, r1 = T / ntx, ty = r1 % nty, r2 = r1 / nty, tz = r2 % ntz, tt = r2 / ntz;
+	const unsigned x = tx * 8 + (tid & 7), y = ty * 8 + ((tid >> 3) & 7), z = tz * 4 + (tid >> 6);
+	return (i64)x + (i64)d.nx * (y + (i64)d.ny * (z + (i64)d.nz * tt));
+}
 static double dot_prod_gpu_order(const float *a, const float *b, i64 N)
 {
 	const i64 cells = N / 4;
@@ -418,13 +429,15 @@ static double dot_prod_gpu_order(const float *a, const float *b, i64 N)
 	const int blocks = (int)(need < cap ? need : cap);
 	const i64 T = (i64)blocks * 256;
 	double *acc = (double *)calloc((size_t)T, sizeof(double));
-	for (i64 c = 0; c < cells; ++c) {
+	const int tiled = g_dot_tiled && g_dot_dims.nx % 8 == 0 && g_dot_dims.ny % 8 == 0 && g_dot_dims.nz % 4 == 0;
+	for (i64 w = 0; w < cells; ++w) {
+		const i64 c = tiled ? gpu_tile_cell(g_dot_dims, w) : w;
 		const float *x = a + c * 4, *y = b + c * 4;
 		double s = (double)(x[0] * y[0]);
 		s += (double)(x[1] * y[1]);
 		s += (double)(x[2] * y[2]);
 		s += (double)(x[3] * y[3]);
-		acc[c % T] += s;
+		acc[w % T] += s;
 	}
 	double *part = (double *)calloc((size_t)blocks, sizeof(double));
 	for (int bl = 0; bl < blocks; ++bl) part[bl] = block_tree(acc + (i64)bl * 256);
