@@ -100,6 +100,7 @@ int flof_halo_exchange(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes, in
 	char *g = (char *)grid;
 	ncclComm_t c = (ncclComm_t)ctx->comm;
 	const size_t n = slice_bytes * (size_t)h;
+	const int pi = flof_prof_pre(ctx, "nccl_halo_sendrecv");
 	FLOF_NCCL(ncclGroupStart());
 	if (ctx->rank > 0) {
 		FLOF_NCCL(ncclSend(g + slice_bytes * (size_t)ta, n, ncclChar, ctx->rank - 1, c, ctx->stream));
@@ -110,6 +111,7 @@ int flof_halo_exchange(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes, in
 		FLOF_NCCL(ncclRecv(g + slice_bytes * (size_t)tb, n, ncclChar, ctx->rank + 1, c, ctx->stream));
 	}
 	FLOF_NCCL(ncclGroupEnd());
+	flof_prof_post(ctx, pi);
 	return FLOF_OK;
 }
 
@@ -118,25 +120,33 @@ int flof_allgather_slabs(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes)
 	if (!flof_sharded(ctx, nt) || ctx->nranks <= 1) return FLOF_OK;
 	char *g = (char *)grid;
 	const size_t n = slice_bytes * (size_t)(ctx->sh.tb - ctx->sh.ta);
+	const int pi = flof_prof_pre(ctx, "nccl_allgather_slabs");
 	FLOF_NCCL(ncclAllGather(g + slice_bytes * (size_t)ctx->sh.ta, g, n, ncclChar, (ncclComm_t)ctx->comm, ctx->stream));
+	flof_prof_post(ctx, pi);
 	return FLOF_OK;
 }
 
 int flof_allreduce_f64_sum(flof_ctx *ctx, double *dev, int n)
 {
 	if (!ctx->comm || ctx->nranks <= 1) return FLOF_OK;
+	const int pi = flof_prof_pre(ctx, "nccl_allreduce_scalar");
 	FLOF_NCCL(ncclAllReduce(dev, dev, n, ncclDouble, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+	flof_prof_post(ctx, pi);
 	return FLOF_OK;
 }
 int flof_allreduce_f32_max(flof_ctx *ctx, float *dev, int n)
 {
 	if (!ctx->comm || ctx->nranks <= 1) return FLOF_OK;
+	const int pi = flof_prof_pre(ctx, "nccl_allreduce_scalar");
 	FLOF_NCCL(ncclAllReduce(dev, dev, n, ncclFloat, ncclMax, (ncclComm_t)ctx->comm, ctx->stream));
+	flof_prof_post(ctx, pi);
 	return FLOF_OK;
 }
 int flof_allreduce_f32_min(flof_ctx *ctx, float *dev, int n)
 {
 	if (!ctx->comm || ctx->nranks <= 1) return FLOF_OK;
+	const int pi = flof_prof_pre(ctx, "nccl_allreduce_scalar");
 	FLOF_NCCL(ncclAllReduce(dev, dev, n, ncclFloat, ncclMin, (ncclComm_t)ctx->comm, ctx->stream));
+	flof_prof_post(ctx, pi);
 	return FLOF_OK;
 }
