@@ -9,6 +9,7 @@
 // (625 taps x 9 instructions per cell for s = 2); the data it touches per pass is still just
 // 16 B in + 16 B out per cell and stays L1/L2 resident across the taps.
 #include <math.h>
+#include <stdlib.h>
 
 #include "flof_common.cuh"
 
@@ -163,17 +164,35 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 {
 	if (sweeps <= 0) return FLOF_OK;
 	const size_t bytes = sizeof(float) * 4 * (size_t)flof_cells(d);
+	const size_t slice_bytes = sizeof(float) * 4 * (size_t)d.nx * d.ny * d.nz;
 	void *tmp = NULL;
 	FLOF_RET(flof_tmp_alloc(ctx, &tmp, bytes, false));
 	float *cur = a, *oth = (float *)tmp;
-	const size_t slice_bytes = sizeof(float) * 4 * (size_t)d.nx * d.ny * d.nz;
-	for (int sIt = 0; sIt < sweeps; ++sIt) {
-		FLOF_RET(flof_halo_exchange(ctx, cur, d.nt, slice_bytes, 1));  // sharded level: +-1 ghost slice per sweep
-		FLOF_RET(flof_launch_expol_tiled(ctx, cur, oth, marker, d));
-		float *sw = cur; cur = oth; oth = sw;
-	}
 	int rc = FLOF_OK;
-	if (cur != a) rc = flof_memcpy_d2d(ctx, a, cur, bytes);
+	const int64_t cap = getenv("FLOF_EXPOL_DENSE") ? 0 : flof_expol_item_capacity(ctx, d);
+	if (cap > 0) {
+		// work-list path: the cells that never change are copied into the second buffer once
+		void *items = NULL, *count = NULL;
+		int n = 0;
+		rc = flof_tmp_alloc(ctx, &items, sizeof(uint32_t) * (size_t)cap, false);
+		if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &count, sizeof(unsigned int), false);
+		if (rc == FLOF_OK) rc = flof_expol_build(ctx, marker, d, (uint32_t *)items, (unsigned int *)count, &n);
+		if (rc == FLOF_OK) rc = flof_memcpy_d2d(ctx, oth, cur, bytes);
+		for (int sIt = 0; sIt < sweeps && rc == FLOF_OK; ++sIt) {
+			rc = flof_halo_exchange(ctx, cur, d.nt, slice_bytes, 1);  // sharded level: +-1 ghost slice per sweep
+			if (rc == FLOF_OK) rc = flof_launch_expol_items(ctx, cur, oth, (const uint32_t *)items, n, d);
+			float *sw = cur; cur = oth; oth = sw;
+		}
+		if (count) flof_tmp_free(ctx, count);
+		if (items) flof_tmp_free(ctx, items);
+	} else {
+		for (int sIt = 0; sIt < sweeps && rc == FLOF_OK; ++sIt) {
+			rc = flof_halo_exchange(ctx, cur, d.nt, slice_bytes, 1);
+			if (rc == FLOF_OK) rc = flof_launch_expol_tiled(ctx, cur, oth, marker, d);
+			float *sw = cur; cur = oth; oth = sw;
+		}
+	}
+	if (rc == FLOF_OK && cur != a) rc = flof_memcpy_d2d(ctx, a, cur, bytes);
 	flof_tmp_free(ctx, tmp);
 	return rc;
 }

@@ -211,6 +211,158 @@ int flof_launch_expol_tiled(flof_ctx *ctx, const float *a, float *tmp, const flo
 	return FLOF_OK;
 }
 
+// ------------------------------------------------------------------ 81-tap extrapolation, work list ---
+// The marker grid is fixed for all sweeps of one corrVelsOf4d pass (ref :770-780) and only cells with
+// marker == 0 ever change: on the synthetic pair ~23 % of the cells, scattered so that 94 % of the
+// 32 x 4 warp patches of the dense kernel contain at least one (tools/expol_probe.py).  So the sweeps
+// run over a compacted list of "items" -- one x, FLOF_ETPY consecutive y, one (z, t) -- built once per
+// pass: every lane of a warp then has arithmetic to do, and the per-sweep `tmp.copyFrom(dst)` of the
+// reference disappears (both ping-pong buffers already hold the cells that never change).
+// item = linear id ((tl*nz + k)*nyb + yb)*nx + x in the low 28 bits, need-mask of the rows in the top 4.
+#define FLOF_EITEM_BITS 28
+
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_expol_build_items(const float *__restrict__ mark, uint32_t *__restrict__ items, unsigned int *__restrict__ count,
+                        flof_kd d, int nyb)
+{
+	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
+	const int k = (int)blockIdx.y, tl = (int)blockIdx.z, t = tl + d.t0;
+	unsigned mask = 0;
+	uint32_t id = 0;
+	if (p < (unsigned)(d.nx * nyb) && k >= 1 && k < d.nz - 1 && t >= 1 && t < d.nt - 1) {
+		const int yb = (int)(p / (unsigned)d.nx), x = (int)(p - (unsigned)yb * (unsigned)d.nx);
+		if (x >= 1 && x < d.nx - 1) {
+			const int64_t plane = flof_idx(d, x, 0, k, t);
+#pragma unroll
+			for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+				const int y = yb * FLOF_ETPY + oy;
+				if (y >= 1 && y < d.ny - 1 && __ldg(mark + plane + (int64_t)y * d.nx) == 0.f) mask |= 1u << oy;
+			}
+		}
+		id = (uint32_t)(((tl * d.nz + k) * nyb + yb) * d.nx + x);
+	}
+	// block-aggregated append: one atomic per CTA, items of a CTA stay in x-fastest order
+	__shared__ unsigned s_off[FLOF_BLOCK / 32], s_base;
+	const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	const unsigned b = __ballot_sync(0xffffffffu, mask != 0);
+	if (lane == 0) s_off[wid] = __popc(b);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned tot = 0;
+		for (int w = 0; w < FLOF_BLOCK / 32; ++w) {
+			const unsigned c = s_off[w];
+			s_off[w] = tot;
+			tot += c;
+		}
+		s_base = tot ? atomicAdd(count, tot) : 0u;
+	}
+	__syncthreads();
+	if (mask) items[s_base + s_off[wid] + __popc(b & ((1u << lane) - 1u))] = id | (mask << FLOF_EITEM_BITS);
+}
+
+template <int MINB, int UNR>
+__global__ void __launch_bounds__(FLOF_BLOCK, MINB)
+    k_cv_expol_items(const float4 *__restrict__ a, float4 *__restrict__ out, const uint32_t *__restrict__ items, int n,
+                     flof_kd d, int nyb)
+{
+	const int q = (int)(blockIdx.x * FLOF_BLOCK + threadIdx.x);
+	if (q >= n) return;
+	const uint32_t it = __ldg(items + q);
+	const unsigned mask = it >> FLOF_EITEM_BITS;
+	unsigned id = it & ((1u << FLOF_EITEM_BITS) - 1u);
+	const int x = (int)(id % (unsigned)d.nx);
+	id /= (unsigned)d.nx;
+	const int y0 = (int)(id % (unsigned)nyb) * FLOF_ETPY;
+	id /= (unsigned)nyb;
+	const int k = (int)(id % (unsigned)d.nz), t = (int)(id / (unsigned)d.nz) + d.t0;
+
+	p4 acc[FLOF_ETPY];
+#pragma unroll
+	for (int oy = 0; oy < FLOF_ETPY; ++oy) acc[oy] = p4_zero();
+	int roff[FLOF_ETPY + 2];  // offset of (x, clamp(y0-1+r)) inside a z-t plane; clamped rows only feed unneeded outputs
+#pragma unroll
+	for (int r = 0; r < FLOF_ETPY + 2; ++r) roff[r] = min(max(y0 - 1 + r, 0), d.ny - 1) * d.nx + x;
+	const int64_t sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
+#pragma unroll(UNR >= 2 ? 3 : 1)
+	for (int vt = t - 1; vt <= t + 1; ++vt) {
+		const float4 *base = a + (sT * vt + sZ * (k - 1));
+#pragma unroll(UNR >= 1 ? 3 : 1)
+		for (int zk = 0; zk < 3; ++zk, base += sZ) {
+			p4 L[FLOF_ETPY + 2][3];
+#pragma unroll
+			for (int r = 0; r < FLOF_ETPY + 2; ++r) {
+				const float4 *row = base + roff[r];
+				L[r][0] = p4_load(row - 1);
+				L[r][1] = p4_load(row);
+				L[r][2] = p4_load(row + 1);
+			}
+#pragma unroll
+			for (int r = 0; r < FLOF_ETPY + 2; ++r)
+#pragma unroll
+				for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+					if (r < oy || r > oy + 2) continue;
+					acc4(acc[oy], L[r][0]);
+					acc4(acc[oy], L[r][1]);
+					acc4(acc[oy], L[r][2]);
+				}
+		}
+	}
+	const double f = 1. / 81.0;
+	float4 *o = out + (sT * t + sZ * k + (int64_t)y0 * d.nx + x);
+#pragma unroll
+	for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+		if (!((mask >> oy) & 1u)) continue;
+		const float4 v = p4_unpack(acc[oy]);
+		o[(int64_t)oy * d.nx] = make_float4((float)(v.x * f), (float)(v.y * f), (float)(v.z * f), (float)(v.w * f));
+	}
+}
+
+// worst-case item count of this rank's slab; 0 = the linear id does not fit FLOF_EITEM_BITS (use the dense kernel)
+static int64_t flof_expol_item_capacity(const flof_ctx *ctx, flof_dim4 d)
+{
+	int ta, tb;
+	flof_slab(ctx, d.nt, &ta, &tb);
+	const int64_t n = (int64_t)d.nx * ((d.ny + FLOF_ETPY - 1) / FLOF_ETPY) * d.nz * (tb - ta);
+	return n < ((int64_t)1 << FLOF_EITEM_BITS) ? n : 0;
+}
+// builds the list into `items` (capacity entries), returns the number of items through *n (host, synchronises once)
+static int flof_expol_build(flof_ctx *ctx, const float *marker, flof_dim4 d, uint32_t *items, unsigned int *count, int *n)
+{
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
+	const int nyb = (d.ny + FLOF_ETPY - 1) / FLOF_ETPY;
+	g.x = (unsigned)(((int64_t)d.nx * nyb + FLOF_BLOCK - 1) / FLOF_BLOCK);
+	FLOF_CK(cudaMemsetAsync(count, 0, sizeof(unsigned int), ctx->stream));
+	FLOF_LAUNCH(k_expol_build_items, g, FLOF_BLOCK, 0, marker, items, count, kd, nyb);
+	unsigned int *h = (unsigned int *)ctx->pinned;
+	FLOF_CK(cudaMemcpyAsync(h, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+	FLOF_CK(cudaStreamSynchronize(ctx->stream));
+	*n = (int)h[0];
+	return FLOF_OK;
+}
+static int flof_launch_expol_items(flof_ctx *ctx, const float *a, float *out, const uint32_t *items, int n, flof_dim4 d)
+{
+	if (n <= 0) return FLOF_OK;
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
+	const int nyb = (d.ny + FLOF_ETPY - 1) / FLOF_ETPY;
+	static int variant = -1;
+	if (variant < 0) variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
+	const dim3 gi((unsigned)((n + FLOF_BLOCK - 1) / FLOF_BLOCK));
+#define FLOF_EI_LAUNCH(MINB, UNR)                                                                                  \
+	FLOF_LAUNCH((k_cv_expol_items<MINB, UNR>), gi, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)out, items, n, kd, nyb)
+	switch (variant) {
+	case 1: FLOF_EI_LAUNCH(2, 1); break;
+	case 2: FLOF_EI_LAUNCH(2, 2); break;
+	case 3: FLOF_EI_LAUNCH(3, 0); break;
+	case 4: FLOF_EI_LAUNCH(3, 1); break;
+	case 5: FLOF_EI_LAUNCH(1, 2); break;
+	case 6: FLOF_EI_LAUNCH(4, 0); break;
+	default: FLOF_EI_LAUNCH(2, 0); break;
+	}
+	return FLOF_OK;
+}
+
 // ------------------------------------------------------------------ Gaussian ---------------
 template <int S> __device__ __forceinline__ int clip_state(int i, int n)
 {  // 0 = window not clipped, 1..S = clipped at the low side by that many taps, S+1..2S = high side
