@@ -162,7 +162,11 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    # rank 0 prints exactly one JSON line on stdout: NCCL writes its version banner / debug lines to fd 1, so
+    # stdout is pointed at stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     from ofblend_b200 import capi, synth
     from ofblend_b200 import dist as fdist
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -303,7 +307,7 @@ def main():
                                     "sample": "%s CPU implementation, one full mode-1 solve on the %d^4 synthetic pair "
                                               "(%.1f s measured), scaled x%d by cell count to %d^4"
                                               % (kind, sample_res, sec, int(scale), res)}
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     barrier()
     ctx.close()
     return 0

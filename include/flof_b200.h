@@ -89,6 +89,9 @@ int flof_ctx_nranks(flof_ctx *ctx);
 int flof_ctx_set_shard_min_cells(flof_ctx *ctx, int64_t cells);
 void flof_slab_range(int nt, int nranks, int rank, int *ta, int *tb); /* slices owned by `rank` */
 int flof_comm_barrier(flof_ctx *ctx);                                 /* stream sync + all ranks */
+/* halos and CG scalars go through NVLink peer mailboxes (IPC-mapped, flof_comm.cu) when every rank could map them;
+ * *enabled tells which path is active, a non-zero *timed_out (also returned as an error) that a peer never arrived */
+int flof_comm_p2p_status(flof_ctx *ctx, int *enabled, int *timed_out);
 int flof_comm_allreduce_max_host(flof_ctx *ctx, double *v);           /* max over ranks of a host scalar */
 
 /* ---- element-wise Grid4d<T> ops (ref: grid4d.h:338-382, grid4d.cpp:213-264) -------------- */

@@ -41,6 +41,25 @@ struct flof_cg_state {
 	int status;        // 0 running, 1 converged, 2 early-out residual0 < eps, 3 sigma == 0 / NaN
 };
 
+// ---- NVLink peer mailboxes (flof_comm.cu): every rank owns one cudaMalloc'ed, IPC-exported buffer that all
+// other ranks map; halos and the CG scalars travel as plain peer stores + system-scope flags.
+#define FLOF_P2P_MAX 16
+struct flof_p2p_dev {           // by-value kernel argument
+	char *peer[FLOF_P2P_MAX];   // mailbox base of every rank in this process's address space (peer[rank] = own)
+	int rank, nranks;
+	unsigned int *err;          // device word, set when a spin-wait timed out
+};
+struct flof_mbox_hdr {
+	unsigned int halo_flag[2][2];  // [0: from rank-1, 1: from rank+1][parity] = sequence number of the data
+	unsigned int pad0[12];
+	struct {
+		double v[4];
+		unsigned int seq;
+		unsigned int pad[7];
+	} ar[2][FLOF_P2P_MAX];         // [parity][source rank]: that rank's contribution to all-reduce #seq
+};
+#define FLOF_MBOX_HDR_BYTES 4096
+
 struct flof_ctx {
 	int device;
 	int sm_count;
@@ -62,6 +81,14 @@ struct flof_ctx {
 	// multi-GPU: one context per rank, NCCL communicator over NVLink (flof_comm.cu)
 	void *comm;              // ncclComm_t
 	int rank, nranks;
+	struct {
+		int enabled;          // 1 = mailboxes mapped on every rank
+		char *mbox;           // own mailbox: header + 4 halo buffers [from][parity] of `cap` bytes
+		size_t cap;
+		flof_p2p_dev dev;
+		unsigned int halo_seq, ar_seq;   // advance identically on every rank (SPMD call sequence)
+		unsigned int *counter;           // device: arrival counter of the push kernel + error word
+	} p2p;
 	int64_t shard_min_cells; // smaller pyramid levels are computed replicated on every rank
 	// t-sharding of the pyramid level currently being processed (set by the multi-scale driver):
 	// every rank keeps full-size grids in a global index space but computes and owns only the

@@ -356,6 +356,7 @@ extern "C" int flof_optical_flow_multiscale4d(flof_ctx *ctx, float *vel, const f
 	FLOF_CK(cudaEventSynchronize(ctx->ev[1]));
 	if (tr) cudaEventElapsedTime(&tr->total_ms, ctx->ev[0], ctx->ev[1]);
 	if (err_out) *err_out = e;
+	if (ctx->nranks > 1) FLOF_RET(flof_comm_p2p_status(ctx, NULL, NULL));  // a timed-out peer wait invalidates the result
 	return FLOF_OK;
 }
 
