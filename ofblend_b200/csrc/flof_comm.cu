@@ -108,24 +108,7 @@ extern "C" int flof_comm_allreduce_max_host(flof_ctx *ctx, double *v)
 // s-1, which that partner issued (stream order) after its own pull of s-2 -- so buffer s&1 is free again.
 // Every spin has a clock64 time-out that raises p2p.dev.err instead of hanging the GPU.
 // NCCL stays for bootstrap (handle exchange), barriers and the bulk all-gathers.
-#define FLOF_SPIN_LIMIT (4000000000ll)  // ~2 s of SM clocks
-
-__device__ __forceinline__ bool p2p_wait(volatile unsigned int *flag, unsigned int seq, unsigned int *err)
-{
-	const long long t0 = clock64();
-	while (*flag != seq) {
-		if (clock64() - t0 > FLOF_SPIN_LIMIT) {
-			atomicExch(err, 1u);
-			return false;
-		}
-	}
-	__threadfence_system();
-	return true;
-}
-__device__ __forceinline__ size_t mbox_buf_off(size_t cap, int from, unsigned int par)
-{
-	return (size_t)FLOF_MBOX_HDR_BYTES + (size_t)(from * 2 + (int)par) * cap;
-}
+#include "flof_p2p.cuh"
 
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_halo_push(flof_p2p_dev pp, const uint4 *__restrict__ lo_src, const uint4 *__restrict__ hi_src, size_t n16, size_t cap,
@@ -184,42 +167,12 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	}
 }
 
-// all-reduce of n <= 4 doubles held in vals[] (one block, >= nranks threads; result in vals[], valid after the call
-// for every thread).  op 0: sum in rank order, 1: max, 2: min.
-__device__ __forceinline__ void p2p_allreduce_block(const flof_p2p_dev &pp, unsigned int seq, double *vals, int n, int op)
-{
-	const unsigned int par = seq & 1u;
-	const int j = (int)threadIdx.x;
-	flof_mbox_hdr *me = (flof_mbox_hdr *)pp.peer[pp.rank];
-	__syncthreads();
-	if (j < pp.nranks) {
-		flof_mbox_hdr *h = (flof_mbox_hdr *)pp.peer[j];
-		volatile double *dv = h->ar[par][pp.rank].v;
-		for (int q = 0; q < n; ++q) dv[q] = vals[q];
-		__threadfence_system();
-		*(volatile unsigned int *)&h->ar[par][pp.rank].seq = seq;
-		p2p_wait(&me->ar[par][j].seq, seq, pp.err);
-	}
-	__syncthreads();
-	if (j == 0) {
-		for (int q = 0; q < n; ++q) {
-			double acc = ((volatile double *)me->ar[par][0].v)[q];
-			for (int r = 1; r < pp.nranks; ++r) {
-				const double x = ((volatile double *)me->ar[par][r].v)[q];
-				acc = op == 0 ? acc + x : (op == 1 ? fmax(acc, x) : fmin(acc, x));
-			}
-			vals[q] = acc;
-		}
-	}
-	__syncthreads();
-}
-
 // stand-alone form on device scalars: kind 0 = n doubles (sum), 1 = n floats (max), 2 = n floats (min)
-__global__ void k_p2p_allreduce(flof_p2p_dev pp, unsigned int seq, void *dev, int n, int kind)
+__global__ void k_p2p_allreduce(flof_p2p_dev pp, void *dev, int n, int kind)
 {
 	__shared__ double vals[4];
 	if ((int)threadIdx.x < n) vals[threadIdx.x] = kind == 0 ? ((double *)dev)[threadIdx.x] : (double)((float *)dev)[threadIdx.x];
-	p2p_allreduce_block(pp, seq, vals, n, kind);
+	p2p_allreduce_block(pp, vals, n, kind == 0 ? n : 0, kind == 2);
 	if ((int)threadIdx.x < n) {
 		if (kind == 0)
 			((double *)dev)[threadIdx.x] = vals[threadIdx.x];
@@ -245,7 +198,7 @@ static void flof_p2p_release(flof_ctx *ctx)
 }
 
 // (re)allocates the mailboxes so that one halo buffer holds `need` bytes; collective over all ranks
-static int flof_p2p_ensure(flof_ctx *ctx, size_t need)
+int flof_p2p_ensure(flof_ctx *ctx, size_t need)
 {
 	static int disabled = -1;
 	if (disabled < 0) disabled = getenv("FLOF_NO_P2P") ? 1 : 0;
@@ -258,8 +211,8 @@ static int flof_p2p_ensure(flof_ctx *ctx, size_t need)
 	const size_t bytes = (size_t)FLOF_MBOX_HDR_BYTES + 4 * cap;
 	FLOF_CK(cudaMalloc((void **)&ctx->p2p.mbox, bytes));
 	FLOF_CK(cudaMemset(ctx->p2p.mbox, 0, FLOF_MBOX_HDR_BYTES));
-	FLOF_CK(cudaMalloc((void **)&ctx->p2p.counter, 2 * sizeof(unsigned int)));
-	FLOF_CK(cudaMemset(ctx->p2p.counter, 0, 2 * sizeof(unsigned int)));
+	FLOF_CK(cudaMalloc((void **)&ctx->p2p.counter, 4 * sizeof(unsigned int)));
+	FLOF_CK(cudaMemset(ctx->p2p.counter, 0, 4 * sizeof(unsigned int)));
 	FLOF_CK(cudaDeviceSynchronize());
 	// exchange the IPC handles through NCCL (device all-gather of 64-byte records)
 	cudaIpcMemHandle_t mine;
@@ -297,9 +250,9 @@ static int flof_p2p_ensure(flof_ctx *ctx, size_t need)
 	ctx->p2p.dev.rank = ctx->rank;
 	ctx->p2p.dev.nranks = ctx->nranks;
 	ctx->p2p.dev.err = ctx->p2p.counter + 1;
+	ctx->p2p.dev.ar_seq = ctx->p2p.counter + 2;
 	ctx->p2p.cap = cap;
 	ctx->p2p.halo_seq = 0;
-	ctx->p2p.ar_seq = 0;
 	ctx->p2p.enabled = ok;
 	if (!ok) disabled = 1;
 	return FLOF_OK;
@@ -372,8 +325,7 @@ static int flof_allreduce_scalar(flof_ctx *ctx, void *dev, int n, int kind)
 	if (!ctx->comm || ctx->nranks <= 1) return FLOF_OK;
 	FLOF_RET(flof_p2p_ensure(ctx, 0));
 	if (ctx->p2p.enabled && n <= 4) {
-		const unsigned int seq = ++ctx->p2p.ar_seq;
-		FLOF_LAUNCH(k_p2p_allreduce, 1, 32, 0, ctx->p2p.dev, seq, dev, n, kind);
+		FLOF_LAUNCH(k_p2p_allreduce, 1, 32, 0, ctx->p2p.dev, dev, n, kind);
 		return FLOF_OK;
 	}
 	const int pi = flof_prof_pre(ctx, "nccl_allreduce_scalar");

@@ -48,6 +48,7 @@ struct flof_p2p_dev {           // by-value kernel argument
 	char *peer[FLOF_P2P_MAX];   // mailbox base of every rank in this process's address space (peer[rank] = own)
 	int rank, nranks;
 	unsigned int *err;          // device word, set when a spin-wait timed out
+	unsigned int *ar_seq;       // device word: sequence number of the last all-reduce
 };
 struct flof_mbox_hdr {
 	unsigned int halo_flag[2][2];  // [0: from rank-1, 1: from rank+1][parity] = sequence number of the data
@@ -86,7 +87,7 @@ struct flof_ctx {
 		char *mbox;           // own mailbox: header + 4 halo buffers [from][parity] of `cap` bytes
 		size_t cap;
 		flof_p2p_dev dev;
-		unsigned int halo_seq, ar_seq;   // advance identically on every rank (SPMD call sequence)
+		unsigned int halo_seq;           // advances identically on every rank (SPMD call sequence)
 		unsigned int *counter;           // device: arrival counter of the push kernel + error word
 	} p2p;
 	int64_t shard_min_cells; // smaller pyramid levels are computed replicated on every rank
@@ -127,6 +128,7 @@ static inline bool flof_sharded(const flof_ctx *ctx, int nt) { return ctx->sh.ac
 
 // communication helpers (flof_comm.cu); all are no-ops when the grid is not sharded
 int flof_halo_exchange(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes, int h);
+int flof_p2p_ensure(flof_ctx *ctx, size_t need);  // collective: maps the peer mailboxes (halo buffers >= need bytes)
 int flof_allgather_slabs(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes);
 int flof_allreduce_f64_sum(flof_ctx *ctx, double *dev, int n);
 int flof_allreduce_f32_max(flof_ctx *ctx, float *dev, int n);

@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include "flof_common.cuh"
+#include "flof_p2p.cuh"
 
 int flof_reset_border_vec4(flof_ctx *ctx, float *vel, flof_dim4 d, int resetBnd);
 int flof_optical_flow4d_ex(flof_ctx *ctx, float *vel, const float *i0, const float *i1, float *rhsT, flof_dim4 d,
@@ -164,10 +165,11 @@ __device__ __forceinline__ void cg_init_finalize(flof_cg_state *st, double s, fl
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_cg_init(float4 *__restrict__ x, float4 *__restrict__ res, float4 *__restrict__ srch,
               const float4 *__restrict__ grad, const float4 *__restrict__ rhs, int64_t cells, float diag,
-              float accuracy, int multi, flof_reduce_scratch *red, flof_cg_state *st)
+              float accuracy, int multi, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	__shared__ double shd[32];
 	__shared__ float shf[32];
+	__shared__ double s_ar[4];
 	double dsum = 0.;
 	float mx = -3.402823466e+38f;
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -196,8 +198,17 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		}
 		s = flof_block_sum(s, shd);
 		m = flof_block_max(m, shf);
+		if (multi == 2) {  // sharded, peer mailboxes: combine the slabs of all ranks right here
+			if (threadIdx.x == 0) {
+				s_ar[0] = s;
+				s_ar[1] = (double)m;
+			}
+			p2p_allreduce_block(pp, s_ar, 2, 1, false);
+			s = s_ar[0];
+			m = (float)s_ar[1];
+		}
 		if (threadIdx.x == 0) {
-			if (multi) {  // raw slab results; the ranks are combined by NCCL, then k_cg_init_finalize runs
+			if (multi == 1) {  // raw slab results; the ranks are combined by NCCL, then k_cg_init_finalize runs
 				st->sigmaNew = s;
 				st->residual = m;
 				st->done = 0;
@@ -208,10 +219,27 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	}
 }
 __global__ void k_cg_init_finalize(float accuracy, flof_cg_state *st) { cg_init_finalize(st, st->sigmaNew, st->residual, accuracy); }
-__global__ void k_cg_update_finalize(flof_cg_state *st)
+// end of an iteration's reductions (ref :311-317, 324): relative residual, stop test, sigma ring.  Runs in the tail
+// of k_cg_update (one thread, after every block has read the state) -- or as its own launch after the NCCL calls.
+__device__ __forceinline__ void cg_advance(flof_cg_state *st, double sigmaNew, float residual, int maxIter)
+{
+	st->sigmaNew = sigmaNew;
+	st->residual = residual;
+	st->relResidual = (float)((double)residual / st->resIni);  // ref :312
+	const int it = st->iter;
+	st->iter = it + 1;  // ret_iterations = iter + 1
+	if ((double)residual <= st->acc) {
+		st->done = 1;
+		st->status = 1;
+		return;
+	}
+	st->sigma[(it + 1) & 1] = sigmaNew;
+	if (it + 1 >= maxIter) st->done = 1;  // ref: loop bound cgMaxIter, returns false
+}
+__global__ void k_cg_update_finalize(int maxIter, flof_cg_state *st)
 {
 	if (st->done) return;
-	st->relResidual = (float)((double)st->residual / st->resIni);
+	cg_advance(st, st->sigmaNew, st->residual, maxIter);
 }
 
 // A: tmp = A * srch (ref applyMat :211-232), partial dot(srch, tmp)
@@ -236,11 +264,12 @@ __device__ __forceinline__ int64_t cg_tile_cell(const cg_tiles &q, int64_t w)
 template <bool TILED>
 __global__ void __launch_bounds__(FLOF_BLOCK, FLOF_APPLY_BLK)
     k_cg_apply(float4 *__restrict__ tmp, const float4 *__restrict__ srch, const float4 *__restrict__ grad,
-               int64_t cells, int64_t sY, int64_t sZ, int64_t sT, float offd, float diag, cg_tiles tiles,
-               flof_reduce_scratch *red, flof_cg_state *st)
+               int64_t cells, int64_t sY, int64_t sZ, int64_t sT, float offd, float diag, cg_tiles tiles, int multi,
+               flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	if (st->done) return;
 	__shared__ double shd[32];
+	__shared__ double s_ar[4];
 	double dsum = 0.;
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < cells; w += stride) {
@@ -284,6 +313,11 @@ __global__ void __launch_bounds__(FLOF_BLOCK, FLOF_APPLY_BLK)
 		double s = 0.;
 		for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += red->dsum[0][b];
 		s = flof_block_sum(s, shd);
+		if (multi == 2) {  // dot(srch, A srch) over all ranks, exchanged through the peer mailboxes by this block
+			if (threadIdx.x == 0) s_ar[0] = s;
+			p2p_allreduce_block(pp, s_ar, 1, 1, false);
+			s = s_ar[0];
+		}
 		if (threadIdx.x == 0) st->alpha1 = s;
 	}
 }
@@ -291,12 +325,13 @@ __global__ void __launch_bounds__(FLOF_BLOCK, FLOF_APPLY_BLK)
 // B: alpha = sigma/alpha1; result += alpha*srch; res -= alpha*tmp; partial max(res), dot(res*precond, res)
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_cg_update(float4 *__restrict__ x, float4 *__restrict__ res, const float4 *__restrict__ srch,
-                const float4 *__restrict__ tmp, const float4 *__restrict__ grad, int64_t cells, float diag,
-                flof_reduce_scratch *red, flof_cg_state *st)
+                const float4 *__restrict__ tmp, const float4 *__restrict__ grad, int64_t cells, float diag, int maxIter,
+                int multi, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	if (st->done) return;
 	__shared__ double shd[32];
 	__shared__ float shf[32];
+	__shared__ double s_ar[4];
 	const double sigma = st->sigma[st->iter & 1];
 	const double alpha = sigma / st->alpha1;  // ref :307-308
 	const double nalpha = -alpha;
@@ -332,50 +367,43 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		}
 		s = flof_block_sum(s, shd);
 		m = flof_block_max(m, shf);
+		if (multi == 2) {  // dot(z, res) summed and max(res) maximised over all ranks in one exchange
+			if (threadIdx.x == 0) {
+				s_ar[0] = s;
+				s_ar[1] = (double)m;
+			}
+			p2p_allreduce_block(pp, s_ar, 2, 1, false);
+			s = s_ar[0];
+			m = (float)s_ar[1];
+		}
 		if (threadIdx.x == 0) {
-			st->sigmaNew = s;
-			st->residual = m;
-			st->relResidual = (float)((double)m / st->resIni);  // ref :312
+			if (multi == 1) {  // raw slab results; NCCL combines them, then k_cg_update_finalize advances the state
+				st->sigmaNew = s;
+				st->residual = m;
+			} else {
+				cg_advance(st, s, m, maxIter);
+			}
 		}
 	}
 }
 
-// C: stop test (ref :314-317), else srch = res*precond + beta*srch (ref :318-323)
+// C: srch = res*precond + beta*srch (ref :318-323); the stop test (ref :314-317) already ran in cg_advance
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_cg_direction(float4 *__restrict__ srch, const float4 *__restrict__ res, const float4 *__restrict__ grad,
-                   int64_t cells, float diag, int maxIter, flof_cg_state *st)
+                   int64_t cells, float diag, flof_cg_state *st)
 {
 	if (st->done) return;
-	const int it = st->iter;
-	const double sigma = st->sigma[it & 1], sigmaNew = st->sigmaNew;
-	const bool converged = ((double)st->residual <= st->acc);
-	if (!converged) {
-		const double beta = sigmaNew / sigma;
-		const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-		for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
-			const float4 r = __ldg(res + c), g = __ldg(grad + c);
-			const float4 pc = precond_of(g, diag);
-			float4 p = srch[c];
-			p.x = axpy1(r.x * pc.x, beta, p.x); p.y = axpy1(r.y * pc.y, beta, p.y);
-			p.z = axpy1(r.z * pc.z, beta, p.z); p.w = axpy1(r.w * pc.w, beta, p.w);
-			srch[c] = p;
-		}
+	const int it = st->iter;  // iterations completed: sigma[it & 1] is the new sigma, the other slot the previous one
+	const double beta = st->sigma[it & 1] / st->sigma[(it - 1) & 1];
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
+		const float4 r = __ldg(res + c), g = __ldg(grad + c);
+		const float4 pc = precond_of(g, diag);
+		float4 p = srch[c];
+		p.x = axpy1(r.x * pc.x, beta, p.x); p.y = axpy1(r.y * pc.y, beta, p.y);
+		p.z = axpy1(r.z * pc.z, beta, p.z); p.w = axpy1(r.w * pc.w, beta, p.w);
+		srch[c] = p;
 	}
-}
-
-// single-thread epilogue of an iteration: advance the device-side CG state (runs after C)
-__global__ void k_cg_advance(int maxIter, flof_cg_state *st)
-{
-	if (st->done) return;
-	const int it = st->iter;
-	st->iter = it + 1;  // ret_iterations = iter + 1
-	if ((double)st->residual <= st->acc) {
-		st->done = 1;
-		st->status = 1;
-		return;
-	}
-	st->sigma[(it + 1) & 1] = st->sigmaNew;
-	if (it + 1 >= maxIter) st->done = 1;  // ref: loop bound cgMaxIter, returns false
 }
 
 // ref :520-529 copy back: vel = result / mDx, optional rhsT = rhs[d=0]
@@ -402,7 +430,12 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 	// before every apply, the three scalars of an iteration are all-reduced over the ranks
 	int64_t c0, c1;
 	flof_flat_range(ctx, cells, &c0, &c1);
-	const int multi = (c1 - c0 != cells && ctx->nranks > 1) ? 1 : 0;
+	int multi = (c1 - c0 != cells && ctx->nranks > 1) ? 1 : 0;  // 1: scalars combined by NCCL, 2: inside the kernels (peer mailboxes)
+	if (multi) {
+		FLOF_RET(flof_p2p_ensure(ctx, 0));
+		if (ctx->p2p.enabled) multi = 2;
+	}
+	const flof_p2p_dev pp = ctx->p2p.dev;
 	const int64_t n = c1 - c0;
 	const int blocks = flof_flat_blocks(ctx, n, 8);
 	float4 *X = (float4 *)x + c0, *R = (float4 *)res + c0, *P = (float4 *)srch + c0, *AP = (float4 *)tmp + c0;
@@ -412,8 +445,8 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 	// compile-time switch; the flat kernel is DRAM-latency bound, not L2-bandwidth bound)
 	const bool tiled = FLOF_APPLY_TILED && (d.nx % 8 == 0) && (d.ny % 8 == 0) && (d.nz % 4 == 0);
 	const cg_tiles tiles = { d.nx / 8, d.ny / 8, d.nz / 4, d.nx, d.ny, d.nz };  // brick traversal of the apply kernel (slab-local t)
-	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, X, R, P, G, B, n, k.diag, accuracy, multi, ctx->red, ctx->cg);
-	if (multi) {
+	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, X, R, P, G, B, n, k.diag, accuracy, multi, pp, ctx->red, ctx->cg);
+	if (multi == 1) {
 		FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
 		FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));
 		FLOF_LAUNCH(k_cg_init_finalize, 1, 1, 0, accuracy, ctx->cg);
@@ -431,20 +464,19 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 			if (multi) FLOF_RET(flof_halo_exchange(ctx, srch, d.nt, slice_bytes, 1));
 			if (tiled)
 				FLOF_LAUNCH(k_cg_apply<true>, blocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, n, sY, sZ, sT, k.offd, k.diag, tiles,
-				            ctx->red, ctx->cg);
+				            multi, pp, ctx->red, ctx->cg);
 			else
 				FLOF_LAUNCH(k_cg_apply<false>, blocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, n, sY, sZ, sT, k.offd, k.diag, tiles,
-				            ctx->red, ctx->cg);
-			if (multi) FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->alpha1, 1));
-			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, X, R, (const float4 *)P, (const float4 *)AP, G, n, k.diag, ctx->red,
-			            ctx->cg);
-			if (multi) {
+				            multi, pp, ctx->red, ctx->cg);
+			if (multi == 1) FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->alpha1, 1));
+			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, X, R, (const float4 *)P, (const float4 *)AP, G, n, k.diag, maxIter, multi,
+			            pp, ctx->red, ctx->cg);
+			if (multi == 1) {
 				FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
 				FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));
-				FLOF_LAUNCH(k_cg_update_finalize, 1, 1, 0, ctx->cg);
+				FLOF_LAUNCH(k_cg_update_finalize, 1, 1, 0, maxIter, ctx->cg);
 			}
-			FLOF_LAUNCH(k_cg_direction, blocks, FLOF_BLOCK, 0, P, (const float4 *)R, G, n, k.diag, maxIter, ctx->cg);
-			FLOF_LAUNCH(k_cg_advance, 1, 1, 0, maxIter, ctx->cg);
+			FLOF_LAUNCH(k_cg_direction, blocks, FLOF_BLOCK, 0, P, (const float4 *)R, G, n, k.diag, ctx->cg);
 		}
 		if (launched >= 32) chunk = 16;
 	}
