@@ -41,6 +41,7 @@ KERNEL_BYTES_PER_CELL = {
     "k_cg_direction": 64,     # res, grad, srch 48 -> srch 16
     "k_gauss_blur4d": 32,     # Vec4 in 16 -> Vec4 out 16 per pass
     "k_cv_expol_blur4d": 36,  # a 16 + marker 4 -> tmp 16 (dense kernel: every cell read and written)
+    "k_cv_expol_planes": 36,  # component-plane work-list kernel (default): same algorithmic sweep
     "k_cv_expol_items": 36,   # work-list kernel: same algorithmic sweep (only marker == 0 cells are recomputed)
     "k_project_cells": 44,    # vel 16, phiOrg 4, phiTarget 4 -> dst 16, marker 4
     "k_semi_lagrange4d<float4>": 48,

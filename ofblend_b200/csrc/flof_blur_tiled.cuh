@@ -363,6 +363,230 @@ static int flof_launch_expol_items(flof_ctx *ctx, const float *a, float *out, co
 	return FLOF_OK;
 }
 
+// ------------------------------------------------------------------ 81-tap extrapolation, component planes ---
+// The work-list kernel above is bound by the L1 data pipe: 162 LDG.128 per item feed 648 packed adds, and every
+// row costs three requests (x-1, x, x+1) that re-read the same lines (ncu: l1tex data-pipe 87 %, fma pipe 27 %).
+// For the sweeps the field is therefore re-laid out as four component planes per t-slice,
+//     S[(((t*4 + c)*nz + z)*ny + y)*nx + x]       (a t-slice keeps the byte size of the Vec4 layout)
+// and an item becomes 4 consecutive x (one aligned LDG.128 of ONE component) times FLOF_ETPY rows: the x-reuse of
+// the 3-wide window now happens in registers, the two edge values come from the neighbouring lanes (items of a
+// warp are consecutive in x) with a predicated scalar load where the neighbour lane holds something else.
+// One request per row instead of three; each output still adds its 81 taps in the reference's order.
+// A CTA = 64 items x 4 components (warp w: component w & 3, items (w >> 2)*32 + lane).
+struct flof_soa_dims { int nx, ny, nz, nt, t0, nxg, nyb; };
+
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_expol_to_planes(const float4 *__restrict__ a, float *__restrict__ s, flof_kd d)
+{
+	int i, j, k, t;
+	if (!flof_cell_ijkt(d, i, j, k, t)) return;
+	const float4 v = __ldg(a + flof_idx(d, i, j, k, t));
+	const int64_t n3 = (int64_t)d.nx * d.ny * d.nz;
+	float *o = s + ((int64_t)t * 4) * n3 + ((int64_t)k * d.ny + j) * d.nx + i;
+	o[0] = v.x; o[n3] = v.y; o[2 * n3] = v.z; o[3 * n3] = v.w;
+}
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_expol_from_planes(float4 *__restrict__ a, const float *__restrict__ s, flof_kd d)
+{
+	int i, j, k, t;
+	if (!flof_cell_ijkt(d, i, j, k, t)) return;
+	const int64_t n3 = (int64_t)d.nx * d.ny * d.nz;
+	const float *o = s + ((int64_t)t * 4) * n3 + ((int64_t)k * d.ny + j) * d.nx + i;
+	a[flof_idx(d, i, j, k, t)] = make_float4(__ldg(o), __ldg(o + n3), __ldg(o + 2 * n3), __ldg(o + 3 * n3));
+}
+
+// item = { id = ((tl*nz + k)*nyb + yb)*nxg + xg,  mask bit (oy*4 + i) = cell (4*xg + i, FLOF_ETPY*yb + oy) is recomputed }
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_expol_build_items4(const float *__restrict__ mark, uint2 *__restrict__ items, unsigned int *__restrict__ count,
+                         flof_soa_dims d)
+{
+	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
+	const int k = (int)blockIdx.y, tl = (int)blockIdx.z, t = tl + d.t0;
+	unsigned mask = 0;
+	uint32_t id = 0;
+	if (p < (unsigned)(d.nxg * d.nyb) && k >= 1 && k < d.nz - 1 && t >= 1 && t < d.nt - 1) {
+		const int yb = (int)(p / (unsigned)d.nxg), xg = (int)(p - (unsigned)yb * (unsigned)d.nxg);
+		const int x0 = 4 * xg;
+		const float *mp = mark + (((int64_t)t * d.nz + k) * d.ny) * d.nx + x0;
+#pragma unroll
+		for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+			const int y = yb * FLOF_ETPY + oy;
+			if (y < 1 || y >= d.ny - 1) continue;
+			const float4 m = __ldg(reinterpret_cast<const float4 *>(mp + (int64_t)y * d.nx));
+			const float mv[4] = { m.x, m.y, m.z, m.w };
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				if (x0 + i >= 1 && x0 + i < d.nx - 1 && mv[i] == 0.f) mask |= 1u << (oy * 4 + i);
+		}
+		id = (uint32_t)(((tl * d.nz + k) * d.nyb + yb) * d.nxg + xg);
+	}
+	__shared__ unsigned s_off[FLOF_BLOCK / 32], s_base;
+	const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	const unsigned b = __ballot_sync(0xffffffffu, mask != 0);
+	if (lane == 0) s_off[wid] = __popc(b);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned tot = 0;
+		for (int w = 0; w < FLOF_BLOCK / 32; ++w) {
+			const unsigned c = s_off[w];
+			s_off[w] = tot;
+			tot += c;
+		}
+		s_base = tot ? atomicAdd(count, tot) : 0u;
+	}
+	__syncthreads();
+	if (mask) items[s_base + s_off[wid] + __popc(b & ((1u << lane) - 1u))] = make_uint2(id, mask);
+}
+
+__device__ __forceinline__ unsigned long long f2_pack(float x, float y)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+	return r;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(FLOF_BLOCK, MINB)
+    k_cv_expol_planes(const float *__restrict__ a, float *__restrict__ out, const uint2 *__restrict__ items, int n,
+                      flof_soa_dims d)
+{
+	static_assert(FLOF_ETPY == 4, "mask layout assumes 4 rows per item");
+	const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	const int comp = (int)(wid & 3u);
+	const int q0 = (int)(blockIdx.x * 64u + (wid >> 2) * 32u);
+	if (q0 >= n) return;  // warp-uniform
+	const int q = q0 + (int)lane;
+	const bool valid = q < n;
+	const uint2 it = __ldg(items + (valid ? q : n - 1));
+	// neighbour lanes hold the x-adjacent groups of the same rows?  (ids are consecutive exactly then)
+	const uint32_t id_l = __shfl_up_sync(0xffffffffu, it.x, 1), id_r = __shfl_down_sync(0xffffffffu, it.x, 1);
+	unsigned id = it.x;
+	const int xg = (int)(id % (unsigned)d.nxg);
+	id /= (unsigned)d.nxg;
+	const int y0 = (int)(id % (unsigned)d.nyb) * FLOF_ETPY;
+	id /= (unsigned)d.nyb;
+	const int k = (int)(id % (unsigned)d.nz), t = (int)(id / (unsigned)d.nz) + d.t0;
+	const int x0 = 4 * xg;
+	const bool adj_l = lane > 0 && id_l + 1u == it.x && xg > 0;
+	const bool adj_r = lane < 31 && id_r == it.x + 1u && xg < d.nxg - 1 && q + 1 < n;
+	const bool ld_l = !adj_l && x0 > 0, ld_r = !adj_r && x0 + 4 < d.nx;  // edge value needs its own load
+
+	unsigned long long acc[FLOF_ETPY][2];
+#pragma unroll
+	for (int oy = 0; oy < FLOF_ETPY; ++oy) acc[oy][0] = acc[oy][1] = 0ull;
+	int roff[FLOF_ETPY + 2];
+#pragma unroll
+	for (int r = 0; r < FLOF_ETPY + 2; ++r) roff[r] = min(max(y0 - 1 + r, 0), d.ny - 1) * d.nx + x0;
+	const int64_t sZ = (int64_t)d.nx * d.ny, n3 = sZ * d.nz, sT = 4 * n3;
+#pragma unroll 1
+	for (int vt = t - 1; vt <= t + 1; ++vt) {
+		const float *base = a + (sT * vt + n3 * comp + sZ * (k - 1));
+#pragma unroll 1
+		for (int zk = 0; zk < 3; ++zk, base += sZ) {
+			float4 m[FLOF_ETPY + 2];
+			float el[FLOF_ETPY + 2], er[FLOF_ETPY + 2];
+#pragma unroll
+			for (int r = 0; r < FLOF_ETPY + 2; ++r) {
+				const float *row = base + roff[r];
+				m[r] = __ldg(reinterpret_cast<const float4 *>(row));
+				el[r] = ld_l ? __ldg(row - 1) : 0.f;
+				er[r] = ld_r ? __ldg(row + 4) : 0.f;
+			}
+#pragma unroll
+			for (int r = 0; r < FLOF_ETPY + 2; ++r) {
+				const float sl = __shfl_up_sync(0xffffffffu, m[r].w, 1), sr = __shfl_down_sync(0xffffffffu, m[r].x, 1);
+				const float l = adj_l ? sl : el[r], rr = adj_r ? sr : er[r];
+				const unsigned long long A = f2_pack(l, m[r].x), B = f2_pack(m[r].x, m[r].y), C = f2_pack(m[r].y, m[r].z),
+				                         D = f2_pack(m[r].z, m[r].w), E = f2_pack(m[r].w, rr);
+#pragma unroll
+				for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+					if (r < oy || r > oy + 2) continue;
+					// outputs x0, x0+1 take (x-1, x, x+1) = A, B, C; outputs x0+2, x0+3 take C, D, E -- xi ascending
+					acc[oy][0] = f2_add(f2_add(f2_add(acc[oy][0], A), B), C);
+					acc[oy][1] = f2_add(f2_add(f2_add(acc[oy][1], C), D), E);
+				}
+			}
+		}
+	}
+	if (!valid) return;
+	const double f = 1. / 81.0;
+	const int64_t cell0 = sT * t + n3 * comp + sZ * k + (int64_t)y0 * d.nx + x0;
+#pragma unroll
+	for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+		const unsigned mrow = (it.y >> (oy * 4)) & 15u;
+		if (!mrow) continue;
+		const int64_t c = cell0 + (int64_t)oy * d.nx;
+		float4 o = __ldg(reinterpret_cast<const float4 *>(a + c));  // cells that are not recomputed keep their value
+		float v0, v1, v2, v3;
+		asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(acc[oy][0]));
+		asm("mov.b64 {%0, %1}, %2;" : "=f"(v2), "=f"(v3) : "l"(acc[oy][1]));
+		if (mrow & 1u) o.x = (float)(v0 * f);
+		if (mrow & 2u) o.y = (float)(v1 * f);
+		if (mrow & 4u) o.z = (float)(v2 * f);
+		if (mrow & 8u) o.w = (float)(v3 * f);
+		*reinterpret_cast<float4 *>(out + c) = o;
+	}
+}
+
+static flof_soa_dims flof_soa_dims_of(const flof_ctx *ctx, flof_dim4 d)
+{
+	int ta, tb;
+	flof_slab(ctx, d.nt, &ta, &tb);
+	flof_soa_dims s = { d.nx, d.ny, d.nz, d.nt, ta, d.nx / 4, (d.ny + FLOF_ETPY - 1) / FLOF_ETPY };
+	return s;
+}
+// worst-case item count of the plane layout; 0 = not applicable (nx not a multiple of 4, or ids exceed 32 bits)
+static int64_t flof_expol_planes_capacity(const flof_ctx *ctx, flof_dim4 d)
+{
+	if (d.nx % 4 != 0 || d.nx < 8) return 0;
+	int ta, tb;
+	flof_slab(ctx, d.nt, &ta, &tb);
+	const int64_t n = (int64_t)(d.nx / 4) * ((d.ny + FLOF_ETPY - 1) / FLOF_ETPY) * d.nz * (tb - ta);
+	return n < ((int64_t)1 << 31) ? n : 0;
+}
+static int flof_expol_planes_build(flof_ctx *ctx, const float *marker, flof_dim4 d, uint2 *items, unsigned int *count, int *n)
+{
+	const flof_soa_dims sd = flof_soa_dims_of(ctx, d);
+	int ta, tb;
+	flof_slab(ctx, d.nt, &ta, &tb);
+	const dim3 g((unsigned)(((int64_t)sd.nxg * sd.nyb + FLOF_BLOCK - 1) / FLOF_BLOCK), (unsigned)d.nz, (unsigned)(tb - ta));
+	FLOF_CK(cudaMemsetAsync(count, 0, sizeof(unsigned int), ctx->stream));
+	FLOF_LAUNCH(k_expol_build_items4, g, FLOF_BLOCK, 0, marker, items, count, sd);
+	unsigned int *h = (unsigned int *)ctx->pinned;
+	FLOF_CK(cudaMemcpyAsync(h, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+	FLOF_CK(cudaStreamSynchronize(ctx->stream));
+	*n = (int)h[0];
+	return FLOF_OK;
+}
+static int flof_expol_to_planes(flof_ctx *ctx, const float *a, float *s, flof_dim4 d)
+{
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
+	FLOF_LAUNCH(k_expol_to_planes, g, FLOF_BLOCK, 0, (const float4 *)a, s, kd);
+	return FLOF_OK;
+}
+static int flof_expol_from_planes(flof_ctx *ctx, float *a, const float *s, flof_dim4 d)
+{
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
+	FLOF_LAUNCH(k_expol_from_planes, g, FLOF_BLOCK, 0, (float4 *)a, s, kd);
+	return FLOF_OK;
+}
+static int flof_launch_expol_planes(flof_ctx *ctx, const float *a, float *out, const uint2 *items, int n, flof_dim4 d)
+{
+	if (n <= 0) return FLOF_OK;
+	const flof_soa_dims sd = flof_soa_dims_of(ctx, d);
+	static int variant = -1;
+	if (variant < 0) variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
+	const dim3 g((unsigned)((n + 63) / 64));
+	switch (variant) {
+	case 1: FLOF_LAUNCH((k_cv_expol_planes<2>), g, FLOF_BLOCK, 0, a, out, items, n, sd); break;
+	case 2: FLOF_LAUNCH((k_cv_expol_planes<4>), g, FLOF_BLOCK, 0, a, out, items, n, sd); break;
+	default: FLOF_LAUNCH((k_cv_expol_planes<3>), g, FLOF_BLOCK, 0, a, out, items, n, sd); break;
+	}
+	return FLOF_OK;
+}
+
 // ------------------------------------------------------------------ Gaussian ---------------
 template <int S> __device__ __forceinline__ int clip_state(int i, int n)
 {  // 0 = window not clipped, 1..S = clipped at the low side by that many taps, S+1..2S = high side

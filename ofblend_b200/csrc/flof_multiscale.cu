@@ -218,6 +218,8 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 		MS_RET(flof_grid_mult_const(ctx, vel, n, 4, two));
 	}
 	ShardScope shard(ctx, d);
+	// peer mailboxes sized once per level for its largest halo (two Vec4 slices: Gaussian blur with s = 2)
+	if (ctx->sh.active) MS_RET(flof_p2p_ensure(ctx, 2 * sizeof(float) * 4 * (size_t)ctx->sh.n3));
 
 	// pre-warp (ref :1011-1018)
 	MS_RET(advect_cfl(ctx, P.cfl, vel, i0warped.f(), d, 1, 1));

@@ -432,7 +432,7 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 	flof_flat_range(ctx, cells, &c0, &c1);
 	int multi = (c1 - c0 != cells && ctx->nranks > 1) ? 1 : 0;  // 1: scalars combined by NCCL, 2: inside the kernels (peer mailboxes)
 	if (multi) {
-		FLOF_RET(flof_p2p_ensure(ctx, 0));
+		FLOF_RET(flof_p2p_ensure(ctx, sizeof(float4) * (size_t)sT));  // before the mailbox addresses are captured below
 		if (ctx->p2p.enabled) multi = 2;
 	}
 	const flof_p2p_dev pp = ctx->p2p.dev;

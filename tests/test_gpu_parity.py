@@ -126,6 +126,19 @@ def test_project_and_expol_bitexact(gpu):
     eq(a[1], b[1])
 
 
+@pytest.mark.parametrize("dims", [(16, 12, 10, 9), (8, 7, 6, 5), (40, 9, 5, 6), (12, 13, 7, 6)])
+def test_expol_work_list_paths_bitexact(gpu, dims):
+    """Random markers make ragged work lists (isolated cells, runs, row ends).  The default Vec4 work-list kernel is
+    checked here; FLOF_EXPOL_MODE=0 in the environment runs the same cases through the component-plane kernel
+    (4 x-cells per lane, edge values from the neighbour lanes), FLOF_EXPOL_MODE=2 through the dense kernel."""
+    sh = (dims[3], dims[2], dims[1], dims[0])
+    rng = np.random.default_rng(dims[0] * 131 + dims[1])
+    for density, sweeps in ((0.25, 3), (0.7, 2), (0.02, 4), (1.0, 1)):
+        a = rnd(sh + (4,), 21, 1.3)
+        mark = (rng.random(sh) >= density).astype(np.float32)   # marker != 0 -> cell keeps its value
+        eq(gpu.cv_expol_blur4d(a, mark, sweeps), port.cv_expol_blur4d(a, mark, sweeps))
+
+
 def test_calc_ls_diff(gpu):
     i0, i1 = sdf_pair(D)
     for bnd in (0, 2):
