@@ -264,7 +264,7 @@ def main():
                "share": stats[q].total_ms / max(tot_ms, 1e-9)}
         if key is not None and stats[q].cells > 0:
             # a sharded level is cut along t: each rank's launch covers cells / world of the level
-            sharded = world > 1 and int(stats[q].cells) >= (1 << 20)
+            sharded = world > 1 and int(stats[q].cells) >= (1 << 22)
             row["cells_per_launch"] = int(stats[q].cells) // (world if sharded else 1)
             row["bytes_per_launch"] = KERNEL_BYTES_PER_CELL[key] * row["cells_per_launch"]
             row["gbs"] = row["bytes_per_launch"] / (row["avg_launch_ms"] * 1e-3) / 1e9
@@ -272,8 +272,20 @@ def main():
         ktab.append(row)
     dom = next((r for r in ktab if "gbs" in r), None)  # ktab is sorted by total time: dominant (kernel, level)
     if dom is not None:
+        # measured DRAM traffic of that kernel: one `ncu --set full` capture per round (profiles/r1_ncu_traffic.json),
+        # per cell, scaled to the cells of this launch
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            tk = next((k for k in tj["kernels"] if dom["kernel"].startswith(k)), None)
+            if tk is not None:
+                traffic = tj["kernels"][tk]["bytes_per_cell"] * dom["cells_per_launch"]
+                traffic_src = "profiles/r1_ncu_traffic.json (ncu --set full at 64^4, %.1f B/cell)" % tj["kernels"][tk]["bytes_per_cell"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "cells_per_launch": dom["cells_per_launch"], "achieved": dom["gbs"],
-                    "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                    "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src,
                     "bytes_per_launch": dom["bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
                     "share_of_step": dom["share"],
                     "how": "CUDA events around every launch on the library stream, %d steps" % prof_steps}
@@ -288,7 +300,7 @@ def main():
                                    "synthetic two-drop 4D SDF pair %d^4" % res,
                        "res": res, "levels": [res >> l for l in range(8) if (res >> l) > 10 and (l == 0 or (res >> (l - 1)) > 20)],
                        "l2": "working set (%d MB of grids) exceeds the 126 MB L2; no explicit flush" % (cells * 4 * 30 // 2 ** 20),
-                       "parallelism": "1 GPU" if world == 1 else "t-sharded over %d GPUs (levels >= 2^20 cells; NCCL halos + all-reduce)" % world},
+                       "parallelism": "1 GPU" if world == 1 else "t-sharded over %d GPUs (levels >= 2^22 cells; halos and CG scalars through NVLink peer mailboxes, NCCL all-gathers)" % world},
             "wall_ms_per_step": wall / args.steps * 1e3,
             "cg_cell_updates_per_s": cg_updates / max(cg_ms * 1e-3, 1e-12),
             "cg_iters": [int(trace.cg_iters[q]) for q in range(min(trace.n_solves, 64))],

@@ -85,7 +85,7 @@ int flof_ctx_comm_init(flof_ctx *ctx, int nranks, int rank, const char id[FLOF_C
 int flof_ctx_comm_destroy(flof_ctx *ctx);
 int flof_ctx_rank(flof_ctx *ctx);
 int flof_ctx_nranks(flof_ctx *ctx);
-/* levels with fewer cells are computed redundantly on every rank instead of being sharded (default 2^20) */
+/* levels with fewer cells are computed redundantly on every rank instead of being sharded (default 2^22) */
 int flof_ctx_set_shard_min_cells(flof_ctx *ctx, int64_t cells);
 void flof_slab_range(int nt, int nranks, int rank, int *ta, int *tb); /* slices owned by `rank` */
 int flof_comm_barrier(flof_ctx *ctx);                                 /* stream sync + all ranks */

@@ -69,7 +69,9 @@ int flof_ctx_create(flof_ctx **out, int device)
 	c->sm_count = prop.multiProcessorCount;
 	c->nranks = 1;
 	c->rank = 0;
-	c->shard_min_cells = (int64_t)1 << 20;
+	// break-even of a CG iteration (replicated: 41 us per Mcell; sharded over P: that / P + ~0.1 ms of halo and
+	// reduction latency) lies near 3-4 Mcells: 32^4 stays replicated, 64^4 and up are cut along t
+	c->shard_min_cells = (int64_t)1 << 22;
 	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CCK(cudaDeviceGetDefaultMemPool(&c->pool, device));
 	uint64_t thr = UINT64_MAX;
