@@ -18,6 +18,7 @@
 // Border rows are identity with zero rhs (ref :424-433): marked by grad.x = NaN so the solver
 // kernels need no index arithmetic at all.
 #include <math.h>
+#include <stdlib.h>
 
 #include "flof_common.cuh"
 #include "flof_p2p.cuh"
@@ -261,8 +262,9 @@ __device__ __forceinline__ int64_t cg_tile_cell(const cg_tiles &q, int64_t w)
 #ifndef FLOF_APPLY_TILED
 #define FLOF_APPLY_TILED 0
 #endif
-template <bool TILED>
-__global__ void __launch_bounds__(FLOF_BLOCK, FLOF_APPLY_BLK)
+// STREAM: grad (read once) and tmp (written once) bypass the L2 residency competition with srch, which is read 9x
+template <bool TILED, bool STREAM = false, int MINB = FLOF_APPLY_BLK>
+__global__ void __launch_bounds__(FLOF_BLOCK, MINB)
     k_cg_apply(float4 *__restrict__ tmp, const float4 *__restrict__ srch, const float4 *__restrict__ grad,
                int64_t cells, int64_t sY, int64_t sZ, int64_t sT, float offd, float diag, cg_tiles tiles, int multi,
                flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK, FLOF_APPLY_BLK)
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < cells; w += stride) {
 		const int64_t c = TILED ? cg_tile_cell(tiles, w) : w;
-		const float4 g = __ldg(grad + c);
+		const float4 g = STREAM ? __ldcs(grad + c) : __ldg(grad + c);
 		const float4 p = __ldg(srch + c);
 		float4 v;
 		if (is_border(g)) {
@@ -304,7 +306,10 @@ __global__ void __launch_bounds__(FLOF_BLOCK, FLOF_APPLY_BLK)
 			}
 			v = make_float4(vv[0], vv[1], vv[2], vv[3]);
 		}
-		tmp[c] = v;
+		if (STREAM)
+			__stcs(tmp + c, v);
+		else
+			tmp[c] = v;
 		dsum += dot4(p, v);
 	}
 	dsum = flof_block_sum(dsum, shd);
@@ -452,6 +457,8 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 		FLOF_LAUNCH(k_cg_init_finalize, 1, 1, 0, accuracy, ctx->cg);
 	}
 	flof_cg_state *h = (flof_cg_state *)ctx->pinned;
+	static int apply_variant = -1;
+	if (apply_variant < 0) apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 1;  // measured: 1 (streaming hints, 4 CTAs/SM) fastest
 	int launched = 0;
 	// poll the device-side done flag every `chunk` iterations; iterations after convergence are
 	// no-op kernels (early return on st->done)
@@ -465,9 +472,21 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 			if (tiled)
 				FLOF_LAUNCH(k_cg_apply<true>, blocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, n, sY, sZ, sT, k.offd, k.diag, tiles,
 				            multi, pp, ctx->red, ctx->cg);
-			else
-				FLOF_LAUNCH(k_cg_apply<false>, blocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, n, sY, sZ, sT, k.offd, k.diag, tiles,
-				            multi, pp, ctx->red, ctx->cg);
+			else {
+#define FLOF_APPLY_LAUNCH(...)                                                                                           \
+	FLOF_LAUNCH((k_cg_apply<__VA_ARGS__>), blocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, n, sY, sZ, sT, k.offd, k.diag, \
+	            tiles, multi, pp, ctx->red, ctx->cg)
+				switch (apply_variant) {
+				case 1: FLOF_APPLY_LAUNCH(false, true, 4); break;
+				case 2: FLOF_APPLY_LAUNCH(false, false, 5); break;
+				case 3: FLOF_APPLY_LAUNCH(false, true, 5); break;
+				case 4: FLOF_APPLY_LAUNCH(false, false, 6); break;
+				case 5: FLOF_APPLY_LAUNCH(false, true, 6); break;
+				case 6: FLOF_APPLY_LAUNCH(false, false, 3); break;
+				case 7: FLOF_APPLY_LAUNCH(false, true, 8); break;
+				default: FLOF_APPLY_LAUNCH(false, false, 4); break;
+				}
+			}
 			if (multi == 1) FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->alpha1, 1));
 			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, X, R, (const float4 *)P, (const float4 *)AP, G, n, k.diag, maxIter, multi,
 			            pp, ctx->red, ctx->cg);
