@@ -138,6 +138,11 @@ int flof_init_test_checkerboard(flof_ctx *ctx, float *val, float *vec4_or_null, 
                                 int brd);
 /* ref: debugGridAvg4d test.cpp:199.  Synchronises. */
 int flof_debug_grid_avg4d(flof_ctx *ctx, const float *phi, flof_dim4 d, int brd, float *out);
+/* ref: debugVelAvg4d test.cpp:210-219 (mean |v| over the bnd region) */
+int flof_debug_vel_avg4d(flof_ctx *ctx, const float *v, flof_dim4 d, int brd, float *out);
+/* ref: calcObfDiff optflow4d.cpp:1762-1777 (3D difference images of two blended results; vel grids are Vec3 AoS) */
+int flof_calc_obf_diff(flof_ctx *ctx, const float *phi1, const float *phi2, float *phiDiff, const float *vel1,
+                       const float *vel2, const float *velt1, const float *velt2, float *velDiff, flof_dim3 d, int bnd);
 
 /* ---- resampling (ref: grid4d.cpp:531-569, grid4d.h:275-283, 463-471; optflow4d.cpp:40-57) - */
 /* host-side helper, pure arithmetic: srcFac out, off in/out (ref: gridFactor4d grid4d.cpp:559) */

@@ -286,6 +286,8 @@ __global__ void k_max_diff(const float *__restrict__ a, const float *__restrict_
 		double dsum = 0.;
 		if (elem == 1) {
 			dsum = (double)fabsf(a[i] - b[i]);
+		} else if (elem == -1) {  // Grid4d<int>, ref grid4dMaxDiffInt grid4d.cpp:429-437
+			dsum = fabs((double)((const int *)a)[i] - (double)((const int *)b)[i]);
 		} else {
 			for (int c = 0; c < elem; ++c) dsum += fabs((double)a[i * elem + c] - (double)b[i * elem + c]);
 		}
@@ -340,6 +342,58 @@ extern "C" int flof_debug_grid_avg4d(flof_ctx *ctx, const float *phi, flof_dim4 
 	FLOF_CK(cudaStreamSynchronize(ctx->stream));
 	const double cnt = (double)(d.nx - 2 * brd) * (d.ny - 2 * brd) * (d.nz - 2 * brd) * (d.nt - 2 * brd);
 	*out = (float)(h[0] * 1000000. / cnt);
+	return FLOF_OK;
+}
+
+// ref: debugVelAvg4d test.cpp:210-219: mean of norm(v) over the bnd region, accumulated in double; norm() snaps to
+// exactly 1 when |l - 1| < eps^2 (util/vector4d.h:304-308).  Debug print only: block partials are combined with atomics.
+__global__ void k_vel_avg(const float4 *__restrict__ v, flof_dim4 d, int brd, flof_reduce_scratch *red)
+{
+	__shared__ double sh[32];
+	int i, j, k, t;
+	double a = 0.;
+	if (flof_cell_ijkt(d, i, j, k, t) && flof_in_bounds(d, i, j, k, t, brd)) {
+		const float4 q = v[flof_idx(d, i, j, k, t)];
+		const float l = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+		a = (fabs((double)l - 1.) < (double)(FLOF_VECTOR_EPSILON * FLOF_VECTOR_EPSILON)) ? 1. : (double)sqrtf(l);
+	}
+	a = flof_block_sum(a, sh);
+	if (threadIdx.x == 0) atomicAdd(&red->out_d[1], a);
+}
+extern "C" int flof_debug_vel_avg4d(flof_ctx *ctx, const float *v, flof_dim4 d, int brd, float *out)
+{
+	FLOF_CK(cudaMemsetAsync(&ctx->red->out_d[1], 0, sizeof(double), ctx->stream));
+	FLOF_LAUNCH(k_vel_avg, flof_grid4(d), FLOF_BLOCK, 0, (const float4 *)v, d, brd, ctx->red);
+	double *h = (double *)ctx->pinned;
+	FLOF_CK(cudaMemcpyAsync(h, &ctx->red->out_d[1], sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	FLOF_CK(cudaStreamSynchronize(ctx->stream));
+	const double cnt = (double)(d.nx - 2 * brd) * (d.ny - 2 * brd) * (d.nz - 2 * brd) * (d.nt - 2 * brd);
+	*out = (float)(h[0] * 1. / cnt);
+	return FLOF_OK;
+}
+
+// ref: calcObfDiff optflow4d.cpp:1762-1777 (3D): phiDiff = |phi1 - phi2|, velDiff = norm((vel1 - vel2, velt1 - velt2))
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_calc_obf_diff(const float *__restrict__ phi1, const float *__restrict__ phi2, float *__restrict__ phiDiff,
+                    const float *__restrict__ vel1, const float *__restrict__ vel2, const float *__restrict__ velt1,
+                    const float *__restrict__ velt2, float *__restrict__ velDiff, flof_dim3 d, int bnd)
+{
+	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
+	if (p >= (unsigned)(d.nx * d.ny)) return;
+	const int j = (int)(p / (unsigned)d.nx), i = (int)(p - (unsigned)j * (unsigned)d.nx), k = (int)blockIdx.y;
+	if (i < bnd || j < bnd || i >= d.nx - bnd || j >= d.ny - bnd) return;
+	if (d.nz > 1 && (k < bnd || k >= d.nz - bnd)) return;  // FOR_IJK_BND: z border only for 3D grids
+	const int64_t c = (int64_t)i + (int64_t)d.nx * (j + (int64_t)d.ny * k);
+	phiDiff[c] = fabsf(phi1[c] - phi2[c]);
+	const float d0 = vel1[3 * c] - vel2[3 * c], d1 = vel1[3 * c + 1] - vel2[3 * c + 1], d2 = vel1[3 * c + 2] - vel2[3 * c + 2];
+	const float d3 = velt1[c] - velt2[c];
+	const float l = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+	velDiff[c] = (fabs((double)l - 1.) < (double)(FLOF_VECTOR_EPSILON * FLOF_VECTOR_EPSILON)) ? 1.f : sqrtf(l);
+}
+extern "C" int flof_calc_obf_diff(flof_ctx *ctx, const float *phi1, const float *phi2, float *phiDiff, const float *vel1,
+                                  const float *vel2, const float *velt1, const float *velt2, float *velDiff, flof_dim3 d, int bnd)
+{
+	FLOF_LAUNCH(k_calc_obf_diff, flof_grid3(d), FLOF_BLOCK, 0, phi1, phi2, phiDiff, vel1, vel2, velt1, velt2, velDiff, d, bnd);
 	return FLOF_OK;
 }
 

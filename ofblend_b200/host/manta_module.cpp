@@ -768,6 +768,24 @@ PYBIND11_MODULE(manta, m)
 	auto maxDiff = [](Grid4 &a, Grid4 &b) { double o = 0.; a.sameSize(b, "grid4dMaxDiff"); CK(flof_grid_max_diff(ctx(), a.f(), b.f(), a.cells, a.elem, &o), "grid4dMaxDiff"); return (float)o; };
 	m.def("grid4dMaxDiff", maxDiff, py::arg("g1"), py::arg("g2"));
 	m.def("grid4dMaxDiffVec4", maxDiff, py::arg("g1"), py::arg("g2"));
+	m.def("grid4dMaxDiffVec3", maxDiff, py::arg("g1"), py::arg("g2"));  // ref grid4d.cpp:439-451 (elem 3: sum of |component diffs|)
+	m.def("grid4dMaxDiffInt", [](Grid4 &a, Grid4 &b) {  // ref grid4d.cpp:429-437
+		      double o = 0.; a.sameSize(b, "grid4dMaxDiffInt"); requireKind(a, K_INT, "grid4dMaxDiffInt", "g1");
+		      CK(flof_grid_max_diff(ctx(), a.f(), b.f(), a.cells, -1, &o), "grid4dMaxDiffInt"); return (float)o;
+	      }, py::arg("g1"), py::arg("g2"));
+	m.def("debugVelAvg4d", [](Grid4 &v, PInt brd) {  // ref test.cpp:210
+		      requireKind(v, K_VEC4, "debugVelAvg4d", "v"); float o = 0.f;
+		      CK(flof_debug_vel_avg4d(ctx(), v.f(), v.d, brd.v, &o), "debugVelAvg4d"); return o;
+	      }, py::arg("v"), py::arg("brd") = PInt{ 0 });
+	m.def("calcObfDiff", [](Grid3 &phi1, Grid3 &phi2, Grid3 &phiDiff, Grid3 &vel1, Grid3 &vel2, Grid3 &velt1, Grid3 &velt2, Grid3 &velDiff, PInt bnd) {
+		      requireKind(phi1, K_REAL, "calcObfDiff", "phi1"); requireKind(phi2, K_REAL, "calcObfDiff", "phi2");
+		      requireKind(phiDiff, K_REAL, "calcObfDiff", "phiDiff"); requireKind(vel1, K_VEC3, "calcObfDiff", "vel1");
+		      requireKind(vel2, K_VEC3, "calcObfDiff", "vel2"); requireKind(velt1, K_REAL, "calcObfDiff", "velt1");
+		      requireKind(velt2, K_REAL, "calcObfDiff", "velt2"); requireKind(velDiff, K_REAL, "calcObfDiff", "velDiff");
+		      phi1.sameSize(phi2, "calcObfDiff"); phi1.sameSize(phiDiff, "calcObfDiff"); vel1.sameSize(vel2, "calcObfDiff");
+		      CK(flof_calc_obf_diff(ctx(), phi1.f(), phi2.f(), phiDiff.f(), vel1.f(), vel2.f(), velt1.f(), velt2.f(), velDiff.f(), phiDiff.d, bnd.v), "calcObfDiff");
+	      }, py::arg("phi1"), py::arg("phi2"), py::arg("phiDiff"), py::arg("vel1"), py::arg("vel2"), py::arg("velt1"), py::arg("velt2"),
+	      py::arg("velDiff"), py::arg("bnd"));
 	m.def("debugGridAvg4d", [](Grid4 &phi, PInt brd) { float o = 0.f; CK(flof_debug_grid_avg4d(ctx(), phi.f(), phi.d, brd.v, &o), "debugGridAvg4d"); return o; }, py::arg("phi"), py::arg("brd") = PInt{ 0 });
 	m.def("initVecFromScalar", [](Grid4 &source, Grid4 &target) { CK(flof_init_vec_from_scalar(ctx(), source.f(), target.f(), source.cells), "initVecFromScalar"); }, py::arg("source"), py::arg("target"));
 	m.def("initTestCheckerboard", [](Grid4 &val, const py::object &vec, PInt brd) {

@@ -1,0 +1,86 @@
+"""The `manta` module (C++ host layer over the C ABI) driven like the reference's own grid tests
+(tools/tests/test_0032_grid4dop.py style): small grids, helper plugins compared with numpy restatements of
+grid4d.cpp:419-452, test.cpp:199-219 and optflow4d.cpp:1762-1777.  Runs in a subprocess because importing
+`manta` creates the process-wide device context."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+SNIPPET = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from manta import *
+rng = np.random.default_rng(7)
+nx, ny, nz, nt = 12, 10, 9, 8
+s4 = Solver(name="t4", gridSize=vec3(nx, ny, nz), dim=3, fourthDim=nt)
+sh = (nt, nz, ny, nx)
+
+def put(g, a):
+    g.fromBytes(np.ascontiguousarray(a).tobytes())
+
+def get(g, shape, dt=np.float32):
+    return np.frombuffer(g.toNumpyBytes(), dtype=dt).reshape(shape)
+
+# grid4dMaxDiff / Vec4 / Vec3 / Int  (ref grid4d.cpp:419-464)
+a, b = s4.create(Grid4Real), s4.create(Grid4Real)
+A, B = rng.standard_normal(sh).astype(np.float32), rng.standard_normal(sh).astype(np.float32)
+put(a, A); put(b, B)
+assert abs(grid4dMaxDiff(a, b) - np.abs(A - B).max()) < 1e-6
+v1, v2 = s4.create(Grid4Vec4), s4.create(Grid4Vec4)
+V1, V2 = rng.standard_normal(sh + (4,)).astype(np.float32), rng.standard_normal(sh + (4,)).astype(np.float32)
+put(v1, V1); put(v2, V2)
+ref4 = np.abs(V1.astype(np.float64) - V2).sum(-1).max()
+assert abs(grid4dMaxDiffVec4(v1, v2) - ref4) < 1e-5 * ref4
+w1, w2 = s4.create(Grid4Vec3), s4.create(Grid4Vec3)
+W1, W2 = rng.standard_normal(sh + (3,)).astype(np.float32), rng.standard_normal(sh + (3,)).astype(np.float32)
+put(w1, W1); put(w2, W2)
+ref3 = np.abs(W1.astype(np.float64) - W2).sum(-1).max()
+assert abs(grid4dMaxDiffVec3(w1, w2) - ref3) < 1e-5 * ref3
+i1, i2 = s4.create(Grid4Int), s4.create(Grid4Int)
+I1, I2 = rng.integers(-50, 50, sh).astype(np.int32), rng.integers(-50, 50, sh).astype(np.int32)
+put(i1, I1); put(i2, I2)
+assert grid4dMaxDiffInt(i1, i2) == float(np.abs(I1.astype(np.int64) - I2).max())
+assert grid4dMaxDiffInt(i1, i1) == 0.0
+
+# debugGridAvg4d / debugVelAvg4d  (ref test.cpp:199-219)
+for brd in (0, 2):
+    sl = (slice(brd, nt - brd), slice(brd, nz - brd), slice(brd, ny - brd), slice(brd, nx - brd))
+    refa = A[sl].astype(np.float64).mean() * 1e6
+    assert abs(debugGridAvg4d(a, brd) - refa) <= 1e-4 * max(1.0, abs(refa))
+    refv = np.sqrt((V1[sl].astype(np.float32) ** 2).sum(-1, dtype=np.float32)).astype(np.float64).mean()
+    assert abs(debugVelAvg4d(v1, brd) - refv) <= 1e-5 * refv
+
+# calcObfDiff  (ref optflow4d.cpp:1762-1777, 3D)
+s3 = Solver(name="t3", gridSize=vec3(nx, ny, nz), dim=3)
+sh3 = (nz, ny, nx)
+p1, p2, pd, vd = s3.create(RealGrid), s3.create(RealGrid), s3.create(RealGrid), s3.create(RealGrid)
+u1, u2, t1, t2 = s3.create(VecGrid), s3.create(VecGrid), s3.create(RealGrid), s3.create(RealGrid)
+P1, P2 = rng.standard_normal(sh3).astype(np.float32), rng.standard_normal(sh3).astype(np.float32)
+U1, U2 = rng.standard_normal(sh3 + (3,)).astype(np.float32), rng.standard_normal(sh3 + (3,)).astype(np.float32)
+T1, T2 = rng.standard_normal(sh3).astype(np.float32), rng.standard_normal(sh3).astype(np.float32)
+for g, x in ((p1, P1), (p2, P2), (u1, U1), (u2, U2), (t1, T1), (t2, T2)):
+    put(g, x)
+pd.setConst(-7.); vd.setConst(-7.)
+bnd = 1
+calcObfDiff(p1, p2, pd, u1, u2, t1, t2, vd, bnd)
+PD, VD = get(pd, sh3), get(vd, sh3)
+inner = (slice(bnd, nz - bnd), slice(bnd, ny - bnd), slice(bnd, nx - bnd))
+assert np.array_equal(PD[inner], np.abs(P1 - P2)[inner])
+d = np.concatenate([U1 - U2, (T1 - T2)[..., None]], -1)
+refn = np.sqrt((d * d).sum(-1, dtype=np.float32))
+assert np.allclose(VD[inner], refn[inner], rtol=2e-7, atol=0)
+mask = np.ones(sh3, bool); mask[inner] = False
+assert (PD[mask] == -7.).all() and (VD[mask] == -7.).all()   # FOR_IJK_BND leaves the border untouched
+print("MANTA_HELPERS_OK")
+"""
+
+
+def test_helper_plugins_match_reference_semantics():
+    host = os.path.join(ROOT, "ofblend_b200", "host")
+    p = subprocess.run([sys.executable, "-c", SNIPPET, host], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0 and "MANTA_HELPERS_OK" in p.stdout, p.stdout[-2000:] + "\n" + p.stderr[-3000:]

@@ -3,7 +3,7 @@
 # Numbers printed by runs under ncu are never bench values.
 TAG=${1:-r1}
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s 14000 -c 4700 --csv -f --log-file gpurun_out/${TAG}_launches_bench64.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 4800 -c 1560 --csv -f --log-file gpurun_out/${TAG}_launches_bench64.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches_bench64.out 2>&1
 echo "launch list rc=$? lines=$(wc -l < gpurun_out/${TAG}_launches_bench64.csv)"
 ncu --set full --import-source on --clock-control none -k regex:k_cg_ -s 30 -c 3 -f -o gpurun_out/${TAG}_full_cg \
