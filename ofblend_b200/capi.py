@@ -139,6 +139,10 @@ class Context:
     def sync(self):
         self._chk(self.lib.flof_sync(self.h))
 
+    def set_option(self, name, value):
+        """Kernel selection knob (all choices bit-identical): expol_mode, expol_variant, apply_variant."""
+        self._chk(self.lib.flof_ctx_set_option(self.h, name.encode(), int(value)))
+
     @property
     def stream(self):
         return self.lib.flof_ctx_stream(self.h)

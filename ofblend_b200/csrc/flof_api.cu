@@ -72,6 +72,9 @@ int flof_ctx_create(flof_ctx **out, int device)
 	// break-even of a CG iteration (replicated: 41 us per Mcell; sharded over P: that / P + ~0.1 ms of halo and
 	// reduction latency) lies near 3-4 Mcells: 32^4 stays replicated, 64^4 and up are cut along t
 	c->shard_min_cells = (int64_t)1 << 22;
+	c->opt.expol_mode = getenv("FLOF_EXPOL_MODE") ? atoi(getenv("FLOF_EXPOL_MODE")) : 1;
+	c->opt.expol_variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
+	c->opt.apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 1;
 	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CCK(cudaDeviceGetDefaultMemPool(&c->pool, device));
 	uint64_t thr = UINT64_MAX;
@@ -107,6 +110,15 @@ const char *flof_last_error(flof_ctx *ctx) { return ctx ? ctx->err : g_create_er
 void *flof_ctx_stream(flof_ctx *ctx) { return (void *)ctx->stream; }
 long long flof_ctx_launch_count(flof_ctx *ctx) { return ctx->launches; }
 int flof_ctx_sm_count(flof_ctx *ctx) { return ctx->sm_count; }
+int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value)
+{
+	FLOF_ARG(name != NULL, "flof_ctx_set_option: name is NULL");
+	if (!strcmp(name, "expol_mode")) ctx->opt.expol_mode = value;
+	else if (!strcmp(name, "expol_variant")) ctx->opt.expol_variant = value;
+	else if (!strcmp(name, "apply_variant")) ctx->opt.apply_variant = value;
+	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_set_option: unknown option '%s'", name);
+	return FLOF_OK;
+}
 int flof_ctx_set_shard_min_cells(flof_ctx *ctx, int64_t cells)
 {
 	ctx->shard_min_cells = cells;

@@ -168,8 +168,7 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 	// 1 (default): Vec4 work list.  0: component planes -- bit-exact too, measured equal (0.24 vs 0.20 ms at 64^4,
 	// 4.1 vs 4.4 ms at 128^4: its scalar edge loads and pair-packing moves eat what the 4-wide x tile saves), kept
 	// selectable for further work.  2: dense kernel (no work list).
-	static int mode = -1;
-	if (mode < 0) mode = getenv("FLOF_EXPOL_MODE") ? atoi(getenv("FLOF_EXPOL_MODE")) : 1;
+	const int mode = ctx->opt.expol_mode;
 	const int64_t cap4 = mode == 0 ? flof_expol_planes_capacity(ctx, d) : 0;
 	const int64_t cap1 = (mode <= 1 && cap4 == 0) ? flof_expol_item_capacity(ctx, d) : 0;
 	void *tmp = NULL, *tmp2 = NULL, *items = NULL, *count = NULL;

@@ -346,8 +346,7 @@ static int flof_launch_expol_items(flof_ctx *ctx, const float *a, float *out, co
 	dim3 g;
 	const flof_kd kd = flof_kdim(ctx, d, &g);
 	const int nyb = (d.ny + FLOF_ETPY - 1) / FLOF_ETPY;
-	static int variant = -1;
-	if (variant < 0) variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
+	const int variant = ctx->opt.expol_variant;
 	const dim3 gi((unsigned)((n + FLOF_BLOCK - 1) / FLOF_BLOCK));
 #define FLOF_EI_LAUNCH(MINB, UNR)                                                                                  \
 	FLOF_LAUNCH((k_cv_expol_items<MINB, UNR>), gi, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)out, items, n, kd, nyb)
@@ -576,8 +575,7 @@ static int flof_launch_expol_planes(flof_ctx *ctx, const float *a, float *out, c
 {
 	if (n <= 0) return FLOF_OK;
 	const flof_soa_dims sd = flof_soa_dims_of(ctx, d);
-	static int variant = -1;
-	if (variant < 0) variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
+	const int variant = ctx->opt.expol_variant;
 	const dim3 g((unsigned)((n + 63) / 64));
 	switch (variant) {
 	case 1: FLOF_LAUNCH((k_cv_expol_planes<2>), g, FLOF_BLOCK, 0, a, out, items, n, sd); break;

@@ -90,6 +90,13 @@ struct flof_ctx {
 		unsigned int halo_seq;           // advances identically on every rank (SPMD call sequence)
 		unsigned int *counter;           // device: arrival counter of the push kernel + error word
 	} p2p;
+	// kernel selection knobs (flof_ctx_set_option; defaults from FLOF_EXPOL_MODE / FLOF_EXPOL_VARIANT /
+	// FLOF_APPLY_VARIANT at context creation).  Every choice is bit-identical; they exist for A/B timing and tests.
+	struct {
+		int expol_mode;     // 1 Vec4 work list (default), 0 component planes, 2 dense kernel
+		int expol_variant;  // register budget / unrolling variant of the chosen extrapolation kernel
+		int apply_variant;  // CG apply: 1 streaming hints (default), 0 plain, 2.. occupancy variants
+	} opt;
 	int64_t shard_min_cells; // smaller pyramid levels are computed replicated on every rank
 	// t-sharding of the pyramid level currently being processed (set by the multi-scale driver):
 	// every rank keeps full-size grids in a global index space but computes and owns only the

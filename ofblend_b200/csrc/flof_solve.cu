@@ -457,8 +457,7 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 		FLOF_LAUNCH(k_cg_init_finalize, 1, 1, 0, accuracy, ctx->cg);
 	}
 	flof_cg_state *h = (flof_cg_state *)ctx->pinned;
-	static int apply_variant = -1;
-	if (apply_variant < 0) apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 1;  // measured: 1 (streaming hints, 4 CTAs/SM) fastest
+	const int apply_variant = ctx->opt.apply_variant;  // measured: 1 (streaming hints, 4 CTAs/SM) fastest
 	int launched = 0;
 	// poll the device-side done flag every `chunk` iterations; iterations after convergence are
 	// no-op kernels (early return on st->done)
