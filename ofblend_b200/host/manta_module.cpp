@@ -19,15 +19,21 @@
 #include <pybind11/stl.h>
 #include <zlib.h>
 
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/flof_b200.h"
@@ -274,8 +280,120 @@ struct UniHeader {  // fileio.cpp:36-43 (288 bytes, natural alignment == packed)
 #pragma pack(pop)
 static_assert(sizeof(UniHeader) == 288, "UniHeader layout");
 
+// ---- overlapped .uni I/O ----------------------------------------------------------------------
+// Mode 3 is I/O bound once the look-up kernel is fast: 180 gz-compressed input slices, 119 gz-compressed output
+// frames.  The reference (fileio.cpp:608-700, 834-1002) compresses and decompresses on the calling thread.  Here a
+// small worker pool does the zlib work: `save` returns after the device->host copy and the frame is deflated and
+// written in the background while the next frame is computed; `loadPlaceGrid4d` inflates its slice files in
+// parallel.  Any access to a file with a pending write waits for it; everything is drained at interpreter exit.
+class IoPool {
+public:
+	static IoPool &get()
+	{
+		static IoPool p;
+		return p;
+	}
+	// runs fn on a worker; `key` (file name, may be empty) lets readers wait for a pending write of that file
+	void submit(const std::string &key, size_t bytes, std::function<void()> fn)
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		if (workers_.empty()) {  // after shutdown (interpreter exit): run inline
+			lk.unlock();
+			fn();
+			return;
+		}
+		cv_done_.wait(lk, [&] { return pendingBytes_ + bytes <= kMaxPendingBytes || pendingBytes_ == 0; });
+		if (!key.empty()) pendingKeys_[key]++;
+		pendingBytes_ += bytes;
+		active_++;
+		jobs_.push_back(Job{ key, bytes, std::move(fn) });
+		cv_job_.notify_one();
+	}
+	void waitKey(const std::string &key)
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		cv_done_.wait(lk, [&] { return pendingKeys_.find(key) == pendingKeys_.end(); });
+		rethrow(lk);
+	}
+	void drain()
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		cv_done_.wait(lk, [&] { return active_ == 0; });
+		rethrow(lk);
+	}
+	void shutdown()
+	{
+		{
+			std::unique_lock<std::mutex> lk(mu_);
+			cv_done_.wait(lk, [&] { return active_ == 0; });
+			stop_ = true;
+			cv_job_.notify_all();
+		}
+		for (auto &t : workers_) t.join();
+		workers_.clear();
+	}
+	int threads() const { return (int)workers_.size(); }
+
+private:
+	struct Job {
+		std::string key;
+		size_t bytes;
+		std::function<void()> fn;
+	};
+	static constexpr size_t kMaxPendingBytes = (size_t)2 << 30;
+	IoPool()
+	{
+		unsigned n = std::thread::hardware_concurrency();
+		n = n == 0 ? 4 : (n > 8 ? 8 : n);
+		for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+	}
+	~IoPool() { shutdown(); }
+	void run()
+	{
+		for (;;) {
+			Job j;
+			{
+				std::unique_lock<std::mutex> lk(mu_);
+				cv_job_.wait(lk, [&] { return stop_ || !jobs_.empty(); });
+				if (jobs_.empty()) return;
+				j = std::move(jobs_.front());
+				jobs_.pop_front();
+			}
+			std::string err;
+			try {
+				j.fn();
+			} catch (const std::exception &e) {
+				err = e.what();
+			}
+			std::unique_lock<std::mutex> lk(mu_);
+			if (!err.empty() && error_.empty()) error_ = err;
+			if (!j.key.empty() && --pendingKeys_[j.key] == 0) pendingKeys_.erase(j.key);
+			pendingBytes_ -= j.bytes;
+			active_--;
+			cv_done_.notify_all();
+		}
+	}
+	void rethrow(std::unique_lock<std::mutex> &)
+	{
+		if (error_.empty()) return;
+		const std::string e = error_;
+		error_.clear();
+		throw std::runtime_error(e);
+	}
+	std::mutex mu_;
+	std::condition_variable cv_job_, cv_done_;
+	std::deque<Job> jobs_;
+	std::map<std::string, int> pendingKeys_;
+	std::vector<std::thread> workers_;
+	std::string error_;
+	size_t pendingBytes_ = 0;
+	int active_ = 0;
+	bool stop_ = false;
+};
+
 static void uniSize(const std::string &name, int &x, int &y, int &z, int *t)
 {  // ref getUniFileSize fileio.cpp:572-597
+	IoPool::get().waitKey(name);
 	x = y = z = 0;
 	gzFile gzf = gzopen(name.c_str(), "rb");
 	if (!gzf) return;
@@ -321,24 +439,38 @@ static void writeUni(const std::string &name, const GridAny &g, int nx, int ny, 
 	head.elementType = g.kind == K_INT ? 0 : (g.kind == K_REAL ? 1 : 2);
 	snprintf(head.info, 256, "%s", "mantaflow flof-b200 (CUDA sm_100a) fp1");
 	head.timestamp = 0;
-	gzFile gzf = gzopen(name.c_str(), "wb1");
-	if (!gzf) errMsg("can't open file " + name);
-	gzwrite(gzf, nt ? "M4T2" : "MNT2", 4);
-	gzwrite(gzf, &head, sizeof(head));
-	if (nt) gzwrite(gzf, &nt, sizeof(int));
-	const std::vector<char> h = g.download();
-	size_t off = 0;
-	while (off < h.size()) {
-		const unsigned chunk = (unsigned)std::min<size_t>(h.size() - off, 1u << 28);
-		gzwrite(gzf, h.data() + off, chunk);
-		off += chunk;
+	// device -> host now (the grid may change right after `save` returns); deflate + write on a worker
+	auto payload = std::make_shared<std::vector<char>>(g.download());
+	const bool fourd = nt > 0;
+	IoPool::get().waitKey(name);  // an older pending write of the same file finishes first
+	{  // create the file now: unwritable paths fail here like in the reference, and the file exists once save() returns
+		FILE *f = fopen(name.c_str(), "wb");
+		if (!f) errMsg("can't open file " + name);
+		fclose(f);
 	}
-	gzclose(gzf);
+	IoPool::get().submit(name, payload->size(), [name, head, nt, fourd, payload]() {
+		gzFile gzf = gzopen(name.c_str(), "wb1");  // level 1 like the reference (fileio.cpp:862)
+		if (!gzf) throw std::runtime_error("can't open file " + name);
+		gzwrite(gzf, fourd ? "M4T2" : "MNT2", 4);
+		gzwrite(gzf, &head, sizeof(head));
+		if (fourd) gzwrite(gzf, &nt, sizeof(int));
+		size_t off = 0;
+		while (off < payload->size()) {
+			const unsigned chunk = (unsigned)std::min<size_t>(payload->size() - off, 1u << 28);
+			if (gzwrite(gzf, payload->data() + off, chunk) <= 0) {
+				gzclose(gzf);
+				throw std::runtime_error("write error on " + name);
+			}
+			off += chunk;
+		}
+		if (gzclose(gzf) != Z_OK) throw std::runtime_error("write error on " + name);
+	});
 }
 static void readUni(const std::string &name, GridAny &g, int nx, int ny, int nz, int nt /* 0 = 3D */)
 {  // ref readGridUni :648 (MNT2 only) / readGrid4dUni :885 (full grid)
 	if (name.find_last_of('.') == std::string::npos) errMsg("file '" + name + "' does not have an extension");
 	debMsg(1, "reading grid " << g.name << " from uni file " << name);
+	IoPool::get().waitKey(name);
 	gzFile gzf = gzopen(name.c_str(), "rb");
 	if (!gzf) errMsg("can't open file " + name);
 	char ID[5] = { 0, 0, 0, 0, 0 };
@@ -420,19 +552,42 @@ static SliceSeq &sliceSeq(const std::string &pattern, int first, int end)
 	s.count = end - first;
 	const size_t n3 = (size_t)x * y * z;
 	CK(flof_malloc(ctx(), &s.data, n3 * 4 * (size_t)s.count), "loadPlaceGrid4d");
-	std::vector<float> h(n3);
-	for (int i = 0; i < s.count; ++i) {
-		snprintf(fn, sizeof(fn), pattern.c_str(), first + i);
-		gzFile gzf = gzopen(fn, "rb");
-		if (!gzf) errMsg(std::string("can't open file ") + fn);
-		char ID[5] = { 0, 0, 0, 0, 0 };
-		gzread(gzf, ID, 4);
-		UniHeader head;
-		if (strcmp(ID, "MNT2") || gzread(gzf, &head, sizeof(head)) != (int)sizeof(head)) { gzclose(gzf); errMsg(std::string("bad uni file ") + fn); }
-		if (head.dimX != x || head.dimY != y || head.dimZ != z || head.bytesPerElement != 4) { gzclose(gzf); errMsg(std::string("grid dim doesn't match in ") + fn); }
-		gzReadAll(gzf, h.data(), n3 * 4, fn);
-		gzclose(gzf);
-		CK(flof_memcpy_h2d(ctx(), (float *)s.data + n3 * i, h.data(), n3 * 4), "loadPlaceGrid4d");
+	// inflate the slice files on the I/O workers, a window of them in flight; upload in file order
+	const int window = 64;
+	for (int b0 = 0; b0 < s.count; b0 += window) {
+		const int nb = std::min(window, s.count - b0);
+		std::vector<std::vector<float>> bufs((size_t)nb);
+		for (int q = 0; q < nb; ++q) {
+			snprintf(fn, sizeof(fn), pattern.c_str(), first + b0 + q);
+			const std::string name(fn);
+			IoPool::get().waitKey(name);
+			std::vector<float> *dst = &bufs[(size_t)q];
+			IoPool::get().submit(std::string(), n3 * 4, [name, dst, n3, x, y, z]() {
+				gzFile gzf = gzopen(name.c_str(), "rb");
+				if (!gzf) throw std::runtime_error("can't open file " + name);
+				char ID[5] = { 0, 0, 0, 0, 0 };
+				gzread(gzf, ID, 4);
+				UniHeader head;
+				if (strcmp(ID, "MNT2") || gzread(gzf, &head, sizeof(head)) != (int)sizeof(head)) { gzclose(gzf); throw std::runtime_error("bad uni file " + name); }
+				if (head.dimX != x || head.dimY != y || head.dimZ != z || head.bytesPerElement != 4) { gzclose(gzf); throw std::runtime_error("grid dim doesn't match in " + name); }
+				dst->resize(n3);
+				char *p = (char *)dst->data();
+				size_t left = n3 * 4;
+				while (left > 0) {
+					const int got = gzread(gzf, p, (unsigned)std::min<size_t>(left, 1u << 30));
+					if (got <= 0) { gzclose(gzf); throw std::runtime_error("can't read file " + name + ": truncated payload"); }
+					p += got;
+					left -= (size_t)got;
+				}
+				gzclose(gzf);
+			});
+		}
+		try {
+			IoPool::get().drain();
+		} catch (const std::exception &e) {
+			errMsg(e.what());
+		}
+		for (int q = 0; q < nb; ++q) CK(flof_memcpy_h2d(ctx(), (float *)s.data + n3 * (size_t)(b0 + q), bufs[(size_t)q].data(), n3 * 4), "loadPlaceGrid4d");
 		CK(flof_sync(ctx()), "loadPlaceGrid4d");
 	}
 	return s;
@@ -626,6 +781,16 @@ PYBIND11_MODULE(manta, m)
 	// ---------------------------------------------------------------- free functions
 	m.def("setDebugLevel", [](PInt level) { g_debug_level = level.v; }, py::arg("level") = PInt{ 1 });
 	m.def("printBuildInfo", []() { py::print("mantaflow flof-b200 (CUDA sm_100a) fp1"); return std::string("flof-b200 fp1"); });
+	// pending background writes: flushed at interpreter exit, or explicitly
+	m.def("flushUniWrites", []() { try { IoPool::get().drain(); } catch (const std::exception &e) { errMsg(e.what()); } });
+	py::module_::import("atexit").attr("register")(py::cpp_function([]() {
+		try {
+			IoPool::get().drain();
+		} catch (const std::exception &e) {
+			fprintf(stderr, "flof-b200: background .uni write failed: %s\n", e.what());
+		}
+		IoPool::get().shutdown();
+	}));
 	m.def("getUniFileSize", [](const std::string &name) { int x, y, z; uniSize(name, x, y, z, nullptr); V3 v; v.x = (float)x; v.y = (float)y; v.z = (float)z; return v; }, py::arg("name"));
 
 	// ref opticalFlowMultiscale4d optflow4d.cpp:2182-2195
@@ -843,6 +1008,7 @@ PYBIND11_MODULE(manta, m)
 		      l.fname = fname1;
 		      const size_t bytes = (size_t)x * y * z * t * 16;
 		      CK(flof_malloc(ctx(), &l.defo, bytes), "loadAdvectTimeSlice_OptInit");
+		      IoPool::get().waitKey(fname1);
 		      gzFile gzf = gzopen(fname1.c_str(), "rb");
 		      if (!gzf) errMsg("can't open file " + fname1);
 		      char ID4[5] = { 0, 0, 0, 0, 0 };
