@@ -86,7 +86,7 @@ int flof_ctx_comm_destroy(flof_ctx *ctx);
 int flof_ctx_rank(flof_ctx *ctx);
 int flof_ctx_nranks(flof_ctx *ctx);
 /* kernel selection knobs, all bit-identical (A/B timing, tests): "expol_mode" 1 Vec4 work list (default) / 0 component
- * planes / 2 dense; "expol_variant", "apply_variant" register-budget variants.  Defaults come from the environment
+ * planes / 2 dense; "expol_variant", "apply_variant" register-budget variants (apply: 7 = default).  Defaults come from the environment
  * variables FLOF_EXPOL_MODE, FLOF_EXPOL_VARIANT, FLOF_APPLY_VARIANT when the context is created. */
 int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value);
 /* levels with fewer cells are computed redundantly on every rank instead of being sharded (default 2^22) */

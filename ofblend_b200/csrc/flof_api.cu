@@ -74,7 +74,7 @@ int flof_ctx_create(flof_ctx **out, int device)
 	c->shard_min_cells = (int64_t)1 << 22;
 	c->opt.expol_mode = getenv("FLOF_EXPOL_MODE") ? atoi(getenv("FLOF_EXPOL_MODE")) : 1;
 	c->opt.expol_variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
-	c->opt.apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 1;
+	c->opt.apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 7;
 	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CCK(cudaDeviceGetDefaultMemPool(&c->pool, device));
 	uint64_t thr = UINT64_MAX;

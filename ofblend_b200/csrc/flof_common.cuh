@@ -95,7 +95,7 @@ struct flof_ctx {
 	struct {
 		int expol_mode;     // 1 Vec4 work list (default), 0 component planes, 2 dense kernel
 		int expol_variant;  // register budget / unrolling variant of the chosen extrapolation kernel
-		int apply_variant;  // CG apply: 1 streaming hints (default), 0 plain, 2.. occupancy variants
+		int apply_variant;  // CG apply: 7 (default) = streaming hints + 8 CTAs/SM (32 registers); 0 plain, 1..6 other occupancy points
 	} opt;
 	int64_t shard_min_cells; // smaller pyramid levels are computed replicated on every rank
 	// t-sharding of the pyramid level currently being processed (set by the multi-scale driver):

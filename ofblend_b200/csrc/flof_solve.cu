@@ -273,9 +273,11 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 	__shared__ double shd[32];
 	__shared__ double s_ar[4];
 	double dsum = 0.;
-	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < cells; w += stride) {
-		const int64_t c = TILED ? cg_tile_cell(tiles, w) : w;
+	// cells < 2^29 (checked by the caller): 32-bit cell indices keep the eight neighbour addresses out of registers
+	const int stride = (int)(gridDim.x * blockDim.x), ncell = (int)cells;
+	const int oY = (int)sY, oZ = (int)sZ, oT = (int)sT;
+	for (int w = (int)(blockIdx.x * blockDim.x + threadIdx.x); w < ncell; w += stride) {
+		const int c = TILED ? (int)cg_tile_cell(tiles, w) : w;
 		const float4 g = STREAM ? __ldcs(grad + c) : __ldg(grad + c);
 		const float4 p = __ldg(srch + c);
 		float4 v;
@@ -285,10 +287,10 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 			v = make_float4(0.f, 0.f, 0.f, 0.f);
 			if (offd != 0.f) {
 				// neighbour order of nbx/nby/nbz/nbt (ref :389-392): t-1, z-1, y-1, x-1, x+1, y+1, z+1, t+1
-				const int64_t o[8] = { -sT, -sZ, -sY, -1, 1, sY, sZ, sT };
+				const int o[8] = { -oT, -oZ, -oY, -1, 1, oY, oZ, oT };
 #pragma unroll
 				for (int m = 0; m < 8; ++m) {
-					const float4 q = __ldg(srch + c + o[m]);
+					const float4 q = __ldg(srch + (c + o[m]));
 					v.x += offd * q.x; v.y += offd * q.y; v.z += offd * q.z; v.w += offd * q.w;
 				}
 			}
@@ -457,7 +459,9 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 		FLOF_LAUNCH(k_cg_init_finalize, 1, 1, 0, accuracy, ctx->cg);
 	}
 	flof_cg_state *h = (flof_cg_state *)ctx->pinned;
-	const int apply_variant = ctx->opt.apply_variant;  // measured: 1 (streaming hints, 4 CTAs/SM) fastest
+	// measured at 64^4 (tools/bench_kernel.py): 7 = streaming hints + 32 registers / 8 CTAs per SM 0.156 ms, against
+	// 0.21-0.22 ms for the 4..6-CTA variants: the kernel is DRAM-latency bound and full occupancy hides it
+	const int apply_variant = ctx->opt.apply_variant;
 	int launched = 0;
 	// poll the device-side done flag every `chunk` iterations; iterations after convergence are
 	// no-op kernels (early return on st->done)

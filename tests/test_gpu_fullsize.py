@@ -57,15 +57,15 @@ def test_cg_apply_variants_same_iterations_and_bits(env):
     """The CG apply variants only change cache hints / occupancy: stopping iteration and solution bits are equal."""
     ctx, i0, i1 = env
     res = {}
-    for v in (0, 1, 2):
+    for v in (0, 1, 7):
         ctx.set_option("apply_variant", v)
         vel = ctx.grid(DIMS, 4)
         it = ctx.optical_flow4d(vel, i0, i1, None, 1e-3, 1e-4, 0., 1e-2, -1.)
         res[v] = (it, vel.download())
         vel.free()
-    ctx.set_option("apply_variant", 1)
-    assert res[0][0] == res[1][0] == res[2][0]
-    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][1], res[2][1])
+    ctx.set_option("apply_variant", 7)
+    assert res[0][0] == res[1][0] == res[7][0]
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][1], res[7][1])
 
 
 def test_identical_inputs_give_zero_deformation(env):
