@@ -4,12 +4,15 @@
 #pragma once
 #include "flof_common.cuh"
 
-#define FLOF_SPIN_LIMIT (4000000000ll)  // ~2 s of SM clocks
+#define FLOF_SPIN_LIMIT (20000000000ll)  // ~10 s of SM clocks: host-side skew between ranks (H2D of 6 GB inputs) stays far below
 
+// The error word is sticky: after the first time-out every later wait returns at once, so a rank that lost its
+// partner finishes its launch queue quickly and the host reports the failure (flof_comm_p2p_status).
 __device__ __forceinline__ bool p2p_wait(volatile unsigned int *flag, unsigned int seq, unsigned int *err)
 {
 	const long long t0 = clock64();
 	while (*flag != seq) {
+		if (*(volatile unsigned int *)err) return false;
 		if (clock64() - t0 > FLOF_SPIN_LIMIT) {
 			atomicExch(err, 1u);
 			return false;

@@ -18,4 +18,4 @@ if [ -z "$SKIP_NCCL" ]; then
 FLOF_NO_P2P=1 timeout 600 $TR --master-port 29631 bench.py --gpus $N --steps 3 --res $RES --no-cpu-baseline > gpurun_out/bench_${TAG}_nccl.json 2> gpurun_out/bench_${TAG}_nccl.err; echo "bench nccl rc=$?"
 python tools/show_bench.py gpurun_out/bench_${TAG}_nccl.json | head -${SHOW:-22}
 fi
-tail -3 gpurun_out/*_${TAG}*.err
+tail -n 3 gpurun_out/*_${TAG}*.err | grep -iE "error|timed out" || true
