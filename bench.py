@@ -306,7 +306,9 @@ def main():
             "cg_iters": [int(trace.cg_iters[q]) for q in range(min(trace.n_solves, 64))],
             "final_error": float(trace.errs[min(trace.n_errs, 64) - 1]) if trace.n_errs else None,
             "gpu_launches": int(launches),
-            "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": cells * 24, "d2h_bytes_per_step": cells * 16,
+            # every rank uploads the (replicated) inputs and downloads the complete deformation: whole-job bytes
+            "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": cells * 24 * world, "d2h_bytes_per_step": cells * 16 * world,
+                    "bytes_per_rank": {"h2d": cells * 24, "d2h": cells * 16},
                     "api": "flof_optical_flow_multiscale4d_host (pinned host buffers)"},
             "clocks": sampler.summary(),
             "roofline": roofline,
