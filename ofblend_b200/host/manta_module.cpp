@@ -297,7 +297,7 @@ public:
 	void submit(const std::string &key, size_t bytes, std::function<void()> fn)
 	{
 		std::unique_lock<std::mutex> lk(mu_);
-		if (workers_.empty()) {  // after shutdown (interpreter exit): run inline
+		if (workers_.empty() || syncIo_) {  // after shutdown (interpreter exit) or FLOF_SYNC_IO=1 (A/B timing): run inline
 			lk.unlock();
 			fn();
 			return;
@@ -343,6 +343,7 @@ private:
 	static constexpr size_t kMaxPendingBytes = (size_t)2 << 30;
 	IoPool()
 	{
+		syncIo_ = getenv("FLOF_SYNC_IO") != nullptr;
 		unsigned n = std::thread::hardware_concurrency();
 		n = n == 0 ? 4 : (n > 8 ? 8 : n);
 		for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
@@ -389,6 +390,7 @@ private:
 	size_t pendingBytes_ = 0;
 	int active_ = 0;
 	bool stop_ = false;
+	bool syncIo_ = false;
 };
 
 static void uniSize(const std::string &name, int &x, int &y, int &z, int *t)
