@@ -297,7 +297,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "flof mode 1 (opticalFlowMultiscale4d, README parameters: wSmooth 1e-3, wEnergy 1e-4, "
                                    "cgAccuracy 1e-2, postVelBlur 4, multiStep 3, minGridSize 20, final projection) on "
-                                   "synthetic two-drop 4D SDF pair %d^4" % res,
+                                   "synthetic two-drop 4D SDF pair %d^4%s" % (res, {64: " (BASELINE.json configs[3])", 128: " (BASELINE.json configs[4])"}.get(res, "")),
                        "res": res, "levels": [res >> l for l in range(8) if (res >> l) > 10 and (l == 0 or (res >> (l - 1)) > 20)],
                        "l2": "working set (%d MB of grids) exceeds the 126 MB L2; no explicit flush" % (cells * 4 * 30 // 2 ** 20),
                        "parallelism": "1 GPU" if world == 1 else "t-sharded over %d GPUs (levels >= 2^22 cells; halos and CG scalars through NVLink peer mailboxes, NCCL all-gathers)" % world},
