@@ -11,10 +11,12 @@
 // One CG iteration = three flat kernels over the cells (224 B/cell/iteration):
 //   A: tmp = A*srch                       (+ partial fp64 dot(srch,tmp))
 //   B: result += alpha*srch; res -= alpha*tmp   (+ partial signed max(res), fp64 dot(res*precond,res))
-//   C: srch = res*precond + beta*srch     (stop test first)
+//   C: srch = res*precond + beta*srch     (the stop test and the state advance ran in the tail of B)
 // Scalars (alpha, beta, sigma, residual) never leave the device: each reducing kernel ends with a
 // "last block finishes" pass that sums the per-block partials in index order (deterministic) and
 // updates the flof_cg_state; the host only polls the `done` flag every few iterations.
+// On a t-sharded level the same tail also all-reduces the partials over the ranks through the NVLink
+// peer mailboxes (flof_p2p.cuh), so reduction + collective are one kernel.
 // Border rows are identity with zero rhs (ref :424-433): marked by grad.x = NaN so the solver
 // kernels need no index arithmetic at all.
 #include <math.h>
