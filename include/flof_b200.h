@@ -89,6 +89,15 @@ int flof_ctx_nranks(flof_ctx *ctx);
  * planes / 2 dense; "expol_variant", "apply_variant" register-budget variants (apply: 7 = default).  Defaults come from the environment
  * variables FLOF_EXPOL_MODE, FLOF_EXPOL_VARIANT, FLOF_APPLY_VARIANT when the context is created. */
 int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value);
+/* "dot_mode": 1 (default, FLOF_DOT_MODE) = the CG's dot products are evaluated in the reference's SEQUENTIAL summation
+ * order, bit for bit (ref: dotProd optflow4d.cpp:234-241 -- `for (i) d += a[i]*b[i]`, fp32 product, fp64 running sum),
+ * which makes the whole mode-1 result bit-identical to the reference; 0 = tree reductions (last bits of the sums differ).
+ * flof_dot_seq is that dot product on its own (tests, tools): kind 0 = sum a[i]*b[i], kind 1 = sum (a[i]*precond(b)[i])*a[i]
+ * with the Jacobi reciprocal diagonal of grad = b (ref: precondInit/precondApply :331-354); `cells` Vec4 cells.
+ * stats[6] = dot products, dirty leaves, raw products, pieces, fallbacks to the plain loop, failed consistency checks. */
+int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag, double *result,
+                 unsigned long long *stats);
+int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats);
 /* levels with fewer cells are computed redundantly on every rank instead of being sharded (default 2^22) */
 int flof_ctx_set_shard_min_cells(flof_ctx *ctx, int64_t cells);
 void flof_slab_range(int nt, int nranks, int rank, int *ta, int *tb); /* slices owned by `rank` */

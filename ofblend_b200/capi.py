@@ -143,6 +143,18 @@ class Context:
         """Kernel selection knob (all choices bit-identical): expol_mode, expol_variant, apply_variant."""
         self._chk(self.lib.flof_ctx_set_option(self.h, name.encode(), int(value)))
 
+    def dot_seq(self, a, b, kind=0, diag=0.0):
+        """CG dot product in the reference's sequential summation order (flof_dot_seq); a, b: device Vec4 grids."""
+        out = C.c_double(0)
+        st = (C.c_ulonglong * 6)()
+        self._chk(self.lib.flof_dot_seq(self.h, a.ptr, b.ptr, C.c_int64(a.cells), int(kind), C.c_float(diag), C.byref(out), st))
+        return out.value, [int(x) for x in st]
+
+    def seq_stats(self):
+        st = (C.c_ulonglong * 6)()
+        self._chk(self.lib.flof_seq_stats(self.h, st))
+        return dict(zip(("dots", "dirty_leaves", "raw_products", "pieces", "fallbacks", "inconsistent"), [int(x) for x in st]))
+
     @property
     def stream(self):
         return self.lib.flof_ctx_stream(self.h)

@@ -10,6 +10,7 @@
 #include "flof_common.cuh"
 
 static char g_create_err[512] = "";
+void flof_seq_release(flof_ctx *ctx);  // flof_solve.cu
 
 int flof_fail(flof_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -75,6 +76,7 @@ int flof_ctx_create(flof_ctx **out, int device)
 	c->opt.expol_mode = getenv("FLOF_EXPOL_MODE") ? atoi(getenv("FLOF_EXPOL_MODE")) : 1;
 	c->opt.expol_variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
 	c->opt.apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 7;
+	c->opt.dot_mode = getenv("FLOF_DOT_MODE") ? atoi(getenv("FLOF_DOT_MODE")) : 1;
 	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CCK(cudaDeviceGetDefaultMemPool(&c->pool, device));
 	uint64_t thr = UINT64_MAX;
@@ -97,6 +99,7 @@ int flof_ctx_destroy(flof_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	flof_ctx_comm_destroy(ctx);
+	flof_seq_release(ctx);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
 	cudaFreeHost(ctx->pinned);
 	cudaFree(ctx->cg);
@@ -116,6 +119,7 @@ int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value)
 	if (!strcmp(name, "expol_mode")) ctx->opt.expol_mode = value;
 	else if (!strcmp(name, "expol_variant")) ctx->opt.expol_variant = value;
 	else if (!strcmp(name, "apply_variant")) ctx->opt.apply_variant = value;
+	else if (!strcmp(name, "dot_mode")) ctx->opt.dot_mode = value;
 	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_set_option: unknown option '%s'", name);
 	return FLOF_OK;
 }

@@ -211,8 +211,8 @@ int flof_p2p_ensure(flof_ctx *ctx, size_t need)
 	const size_t bytes = (size_t)FLOF_MBOX_HDR_BYTES + 4 * cap;
 	FLOF_CK(cudaMalloc((void **)&ctx->p2p.mbox, bytes));
 	FLOF_CK(cudaMemset(ctx->p2p.mbox, 0, FLOF_MBOX_HDR_BYTES));
-	FLOF_CK(cudaMalloc((void **)&ctx->p2p.counter, 4 * sizeof(unsigned int)));
-	FLOF_CK(cudaMemset(ctx->p2p.counter, 0, 4 * sizeof(unsigned int)));
+	FLOF_CK(cudaMalloc((void **)&ctx->p2p.counter, 8 * sizeof(unsigned int)));
+	FLOF_CK(cudaMemset(ctx->p2p.counter, 0, 8 * sizeof(unsigned int)));
 	FLOF_CK(cudaDeviceSynchronize());
 	// exchange the IPC handles through NCCL (device all-gather of 64-byte records)
 	cudaIpcMemHandle_t mine;
@@ -251,6 +251,7 @@ int flof_p2p_ensure(flof_ctx *ctx, size_t need)
 	ctx->p2p.dev.nranks = ctx->nranks;
 	ctx->p2p.dev.err = ctx->p2p.counter + 1;
 	ctx->p2p.dev.ar_seq = ctx->p2p.counter + 2;
+	ctx->p2p.dev.chain_seq = ctx->p2p.counter + 3;
 	ctx->p2p.cap = cap;
 	ctx->p2p.halo_seq = 0;
 	ctx->p2p.enabled = ok;

@@ -49,6 +49,7 @@ struct flof_p2p_dev {           // by-value kernel argument
 	int rank, nranks;
 	unsigned int *err;          // device word, set when a spin-wait timed out
 	unsigned int *ar_seq;       // device word: sequence number of the last all-reduce
+	unsigned int *chain_seq;    // device word: sequence number of the last sequential-order dot product (flof_seqsum)
 };
 struct flof_mbox_hdr {
 	unsigned int halo_flag[2][2];  // [0: from rank-1, 1: from rank+1][parity] = sequence number of the data
@@ -58,9 +59,17 @@ struct flof_mbox_hdr {
 		unsigned int seq;
 		unsigned int pad[7];
 	} ar[2][FLOF_P2P_MAX];         // [parity][source rank]: that rank's contribution to all-reduce #seq
+	// sequential-order dot products (flof_seqsum_kernels.cuh): the exact running sum travels rank 0 -> 1 -> ... (chain),
+	// the last rank stores the total into every rank's `total` slot
+	struct {
+		double v;
+		unsigned int seq;
+		unsigned int pad[5];
+	} chain[2], total[2];          // [parity]
 };
 #define FLOF_MBOX_HDR_BYTES 4096
 
+struct flof_seq;
 struct flof_ctx {
 	int device;
 	int sm_count;
@@ -68,6 +77,7 @@ struct flof_ctx {
 	cudaMemPool_t pool;
 	flof_reduce_scratch *red;  // device
 	flof_cg_state *cg;         // device
+	struct flof_seq *seq;      // sequential-order dot products: descriptors, leaf records, piece pool (flof_seqsum.cuh)
 	void *pinned;              // 4 KB pinned host scratch for scalar read-back
 	cudaEvent_t ev[4];
 	long long launches;
@@ -96,6 +106,8 @@ struct flof_ctx {
 		int expol_mode;     // 1 Vec4 work list (default), 0 component planes, 2 dense kernel
 		int expol_variant;  // register budget / unrolling variant of the chosen extrapolation kernel
 		int apply_variant;  // CG apply: 7 (default) = streaming hints + 8 CTAs/SM (32 registers); 0 plain, 1..6 other occupancy points
+		int dot_mode;       // CG dot products: 1 (default) = the reference's sequential summation order, bit for bit
+		                    // (flof_seqsum); 0 = tree reductions (faster, last bits of the fp64 sums differ)
 	} opt;
 	int64_t shard_min_cells; // smaller pyramid levels are computed replicated on every rank
 	// t-sharding of the pyramid level currently being processed (set by the multi-scale driver):

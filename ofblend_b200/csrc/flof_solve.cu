@@ -168,7 +168,7 @@ __device__ __forceinline__ void cg_init_finalize(flof_cg_state *st, double s, fl
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_cg_init(float4 *__restrict__ x, float4 *__restrict__ res, float4 *__restrict__ srch,
               const float4 *__restrict__ grad, const float4 *__restrict__ rhs, int64_t cells, float diag,
-              float accuracy, int multi, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
+              float accuracy, int multi, int defer, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	__shared__ double shd[32];
 	__shared__ float shf[32];
@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 			m = (float)s_ar[1];
 		}
 		if (threadIdx.x == 0) {
-			if (multi == 1) {  // raw slab results; the ranks are combined by NCCL, then k_cg_init_finalize runs
+			if (multi == 1 || defer) {
+				// multi == 1: raw slab results; the ranks are combined by NCCL, then k_cg_init_finalize runs
+				// defer: sigma comes from the sequential-order dot product (k_seq_resolve finalizes the state)
 				st->sigmaNew = s;
 				st->residual = m;
 				st->done = 0;
@@ -244,6 +246,8 @@ __global__ void k_cg_update_finalize(int maxIter, flof_cg_state *st)
 	if (st->done) return;
 	cg_advance(st, st->sigmaNew, st->residual, maxIter);
 }
+
+#include "flof_seqsum_kernels.cuh"
 
 // A: tmp = A * srch (ref applyMat :211-232), partial dot(srch, tmp)
 // TILED: the 256 cells a CTA handles per step form a compact 8 x 8 x 4 (x,y,z) brick instead of 256
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_cg_update(float4 *__restrict__ x, float4 *__restrict__ res, const float4 *__restrict__ srch,
                 const float4 *__restrict__ tmp, const float4 *__restrict__ grad, int64_t cells, float diag, int maxIter,
-                int multi, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
+                int multi, int defer, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	if (st->done) return;
 	__shared__ double shd[32];
@@ -386,7 +390,9 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 			m = (float)s_ar[1];
 		}
 		if (threadIdx.x == 0) {
-			if (multi == 1) {  // raw slab results; NCCL combines them, then k_cg_update_finalize advances the state
+			if (multi == 1 || defer) {
+				// multi == 1: raw slab results; NCCL combines them, then k_cg_update_finalize advances the state
+				// defer: dot(tmp, res) comes from the sequential-order dot product, whose tail advances the state
 				st->sigmaNew = s;
 				st->residual = m;
 			} else {
@@ -428,6 +434,114 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	}
 }
 
+// ---- host side of the sequential-order dot products ---------------------------------------------------------------
+void flof_seq_release(flof_ctx *ctx)
+{
+	flof_seq *q = ctx->seq;
+	if (!q) return;
+	cudaFree(q->desc);
+	cudaFree(q->leaf);
+	cudaFree(q->pool);
+	cudaFree(q->ctl);
+	free(q);
+	ctx->seq = NULL;
+}
+static int seq_ensure(flof_ctx *ctx, int64_t nleaf)
+{
+	flof_seq *q = ctx->seq;
+	if (!q) {
+		q = (flof_seq *)calloc(1, sizeof(flof_seq));
+		if (!q) return flof_fail(ctx, FLOF_ERR_NOMEM, "flof_seq: out of host memory");
+		ctx->seq = q;
+		FLOF_CK(cudaMalloc((void **)&q->pool, sizeof(seq_rec) * (size_t)SEQ_POOL));
+		FLOF_CK(cudaMalloc((void **)&q->ctl, sizeof(seq_ctl)));
+		FLOF_CK(cudaMemset(q->ctl, 0, sizeof(seq_ctl)));
+		FLOF_CK(cudaFuncSetAttribute(k_seq_resolve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_RESOLVE_SMEM));
+		FLOF_CK(cudaFuncSetAttribute(k_seq_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_RESOLVE_SMEM));
+	}
+	if (nleaf > q->cap_leaves) {
+		FLOF_CK(cudaStreamSynchronize(ctx->stream));
+		if (q->desc) cudaFree(q->desc);
+		if (q->leaf) cudaFree(q->leaf);
+		q->desc = NULL;
+		q->leaf = NULL;
+		q->cap_leaves = 0;
+		FLOF_CK(cudaMalloc((void **)&q->desc, sizeof(seq_desc) * (size_t)nleaf));
+		FLOF_CK(cudaMalloc((void **)&q->leaf, sizeof(seq_rec) * (size_t)nleaf));
+		FLOF_CK(cudaMemset(q->desc, 0, sizeof(seq_desc) * (size_t)nleaf));  // stamps 0: no epoch
+		q->cap_leaves = nleaf;
+		q->epoch = 0;
+	}
+	return FLOF_OK;
+}
+// enqueues one dot product over `ncells` cells starting at a / b; total_products = 4 * cells of ALL ranks (error margin)
+static int seq_dot(flof_ctx *ctx, int kind, const float4 *a, const float4 *b, int64_t ncells, float diag, int mode,
+                   float accuracy, int maxIter, flof_cg_state *st, int64_t total_products, int multi, const double *off)
+{
+	const int64_t nleaf = (ncells + SEQ_LEAF_CELLS - 1) / SEQ_LEAF_CELLS;
+	FLOF_ARG(ncells > 0 && ncells < ((int64_t)1 << 31), "flof_seq: cell count out of range");
+	FLOF_RET(seq_ensure(ctx, nleaf));
+	flof_seq *q = ctx->seq;
+	seq_args A;
+	A.desc = q->desc; A.leaf = q->leaf; A.pool = q->pool; A.ctl = q->ctl; A.off = off;
+	A.epoch = ++q->epoch;
+	A.nleaf = (int)nleaf;
+	A.ncells = (int)ncells;
+	A.kf = seq_margin_factor(total_products);
+	int64_t cap = (int64_t)ctx->sm_count * 6;
+	const int blocks = (int)(nleaf < cap ? nleaf : cap);
+	const flof_p2p_dev pp = ctx->p2p.dev;
+	if (kind == 0) {
+		FLOF_LAUNCH(k_dot_seq<0>, blocks, FLOF_BLOCK, 0, a, b, diag, A, st);
+		FLOF_LAUNCH(k_seq_resolve<0>, 1, FLOF_BLOCK, SEQ_RESOLVE_SMEM, a, b, diag, A, mode, accuracy, maxIter, st, multi, pp);
+	} else {
+		FLOF_LAUNCH(k_dot_seq<1>, blocks, FLOF_BLOCK, 0, a, b, diag, A, st);
+		FLOF_LAUNCH(k_seq_resolve<1>, 1, FLOF_BLOCK, SEQ_RESOLVE_SMEM, a, b, diag, A, mode, accuracy, maxIter, st, multi, pp);
+	}
+	return FLOF_OK;
+}
+
+// test / tool entry: the sequential-order sum of a[i]*b[i] (kind 0) or (a[i]*precond(b)[i])*a[i] (kind 1) over
+// `cells` Vec4 cells.  stats (optional, 6 values): dots, dirty leaves, raw products, pieces, fallbacks, inconsistencies
+// since the context was created.
+extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag,
+                            double *result, unsigned long long *stats)
+{
+	FLOF_ARG(kind == 0 || kind == 1, "flof_dot_seq: kind must be 0 or 1");
+	FLOF_RET(seq_dot(ctx, kind, (const float4 *)a, (const float4 *)b, cells, diag, SEQ_MODE_NONE, 0.f, 0, NULL, 4 * cells, 0, NULL));
+	seq_ctl *h = (seq_ctl *)malloc(sizeof(seq_ctl));
+	if (!h) return flof_fail(ctx, FLOF_ERR_NOMEM, "flof_dot_seq: out of host memory");
+	cudaError_t e = cudaMemcpyAsync(h, ctx->seq->ctl, sizeof(seq_ctl), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess) {
+		if (result) *result = h->result;
+		if (stats) {
+			stats[0] = h->n_dots; stats[1] = h->n_dirty; stats[2] = h->n_raw;
+			stats[3] = h->n_pieces; stats[4] = h->n_fallback; stats[5] = h->n_inconsistent;
+		}
+	}
+	free(h);
+	if (e != cudaSuccess) return flof_fail(ctx, FLOF_ERR_CUDA, "flof_dot_seq: %s", cudaGetErrorString(e));
+	return FLOF_OK;
+}
+extern "C" int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats)
+{
+	FLOF_ARG(stats != NULL, "flof_seq_stats: stats is NULL");
+	for (int i = 0; i < 6; ++i) stats[i] = 0;
+	if (!ctx->seq) return FLOF_OK;
+	seq_ctl *h = (seq_ctl *)malloc(sizeof(seq_ctl));
+	if (!h) return flof_fail(ctx, FLOF_ERR_NOMEM, "flof_seq_stats: out of host memory");
+	cudaError_t e = cudaMemcpyAsync(h, ctx->seq->ctl, sizeof(seq_ctl), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess) {
+		stats[0] = h->n_dots; stats[1] = h->n_dirty; stats[2] = h->n_raw;
+		stats[3] = h->n_pieces; stats[4] = h->n_fallback; stats[5] = h->n_inconsistent;
+	}
+	free(h);
+	if (e != cudaSuccess) return flof_fail(ctx, FLOF_ERR_CUDA, "flof_seq_stats: %s", cudaGetErrorString(e));
+	return FLOF_OK;
+}
+
 static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, const float *grad,
                   const float *rhs, flof_dim4 d, float wSmooth, float wEnergy, float accuracy,
                   int maxIter, int *iters, float *relRes, int *status)
@@ -454,7 +568,11 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 	// compile-time switch; the flat kernel is DRAM-latency bound, not L2-bandwidth bound)
 	const bool tiled = FLOF_APPLY_TILED && (d.nx % 8 == 0) && (d.ny % 8 == 0) && (d.nz % 4 == 0);
 	const cg_tiles tiles = { d.nx / 8, d.ny / 8, d.nz / 4, d.nx, d.ny, d.nz };  // brick traversal of the apply kernel (slab-local t)
-	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, X, R, P, G, B, n, k.diag, accuracy, multi, pp, ctx->red, ctx->cg);
+	// dot products in the reference's sequential order (default, single GPU): the reducing kernels keep their max /
+	// tree sums but leave the state alone (defer); k_dot_seq + k_seq_resolve deliver the exact sums and advance it
+	const int seq = (ctx->opt.dot_mode == 1 && !multi) ? 1 : 0;
+	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, X, R, P, G, B, n, k.diag, accuracy, multi, seq, pp, ctx->red, ctx->cg);
+	if (seq) FLOF_RET(seq_dot(ctx, 1, R, G, n, k.diag, SEQ_MODE_INIT, accuracy, maxIter, ctx->cg, 4 * cells, 0, NULL));
 	if (multi == 1) {
 		FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
 		FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));
@@ -493,8 +611,10 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 				}
 			}
 			if (multi == 1) FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->alpha1, 1));
+			if (seq) FLOF_RET(seq_dot(ctx, 0, P, AP, n, k.diag, SEQ_MODE_ALPHA, accuracy, maxIter, ctx->cg, 4 * cells, 0, NULL));
 			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, X, R, (const float4 *)P, (const float4 *)AP, G, n, k.diag, maxIter, multi,
-			            pp, ctx->red, ctx->cg);
+			            seq, pp, ctx->red, ctx->cg);
+			if (seq) FLOF_RET(seq_dot(ctx, 1, R, G, n, k.diag, SEQ_MODE_ADVANCE, accuracy, maxIter, ctx->cg, 4 * cells, 0, NULL));
 			if (multi == 1) {
 				FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
 				FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));

@@ -452,6 +452,27 @@ static double dot_prod_gpu_order(const float *a, const float *b, i64 N)
 	free(part);
 	return r;
 }
+/* test probes for the CUDA path's sequential-order dot products (flof_dot_seq): the reference's loops, nothing else.
+ * kind 0: dotProd(a, b) (:234-241).  kind 1: precondInit + precondApply + dotProd(tmp, res) (:331-354, :296, :319) with
+ * a = res and the Jacobi diagonal of the matrix-free form: grad_d^2 + diag, 1 on identity rows (grad.x = NaN marker). */
+double orc_dot_seq(const float *a, const float *b, long long cells, int kind, float diag)
+{
+	double d = 0.;
+	for (i64 c = 0; c < cells; ++c)
+		for (int q = 0; q < 4; ++q) {
+			const i64 i = c * 4 + q;
+			if (kind == 0) {
+				d += a[i] * b[i];
+			} else {
+				const float g = b[i];
+				float pc = 1.f;
+				if (b[c * 4] == b[c * 4]) pc = 1. / (g * g + diag);
+				const float t = a[i] * pc;
+				d += t * a[i];
+			}
+		}
+	return d;
+}
 static double dot_prod(const float *a, const float *b, i64 N)
 {
 	if (g_dot_mode == 2) return dot_prod_gpu_order(a, b, N);

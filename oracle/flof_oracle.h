@@ -28,6 +28,8 @@ int orc_set_threads(int n);
  * 2 the CUDA kernels' reduction order for a GPU with orc_set_gpu_sm_count() SMs (default 148) */
 void orc_set_dot_mode(int m);
 void orc_set_gpu_sm_count(int n);
+/* the reference's sequential dot-product loops on their own (checker of flof_dot_seq) */
+double orc_dot_seq(const float *a, const float *b, long long cells, int kind, float diag);
 
 /* vector4d.h:488 interpol4d / interpol.h:101 interpol (elem = 1 or 4 floats per cell) */
 void orc_interpol4d(const float *data, orc_dim4 d, int elem, const float pos[4], float *out);

@@ -33,6 +33,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.orc_calc_ls_diff4d.restype = C.c_float
         _lib.orc_optical_flow_multiscale4d.restype = C.c_float
+        _lib.orc_dot_seq.restype = C.c_double
     return _lib
 
 
@@ -304,3 +305,10 @@ def load_advect_time_slice(defo, d3, phi, time, blendAlpha, loadTimeScale, defoO
         _f4(defoOffset), _f4(defoScale), _f4(defoFactor), _f4(overrideSize),
         C.c_float(overrideTimeOff), int(bordSkip), C.c_float(defoAniFac))
     return out
+
+
+def dot_seq(a, b, kind=0, diag=0.0):
+    """The reference's sequential dot-product loop (dotProd, optflow4d.cpp:234-241) on Vec4 arrays; kind 1 applies the
+    Jacobi preconditioner of grad = b first (precondApply :345-351)."""
+    a, b = _f32(a), _f32(b)
+    return float(lib().orc_dot_seq(_p(a), _p(b), C.c_longlong(a.size // 4), int(kind), C.c_float(diag)))
