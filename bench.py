@@ -13,8 +13,14 @@ One JSON line:
                H2D of i0, i1, vel from pinned memory and D2H of the deformation inside the timed region
   roofline     dominant kernel: algorithmic bytes per launch / its average duration, measured live with
                CUDA events bracketing every launch (flof_profile_begin/end) in K extra steps
-  cpu_baseline the reference's own CPU implementation (oracle/_ref, else our C port) on a bounded sample
---impl reference times that CPU implementation as the reference arm.
+  cpu_baseline the reference's own CPU implementation (oracle/_ref, else our C port) on a bounded sample of the SAME
+               64^4 workload: the first finest-level opticalFlow4d solve (assembly + CG), scaled by CG cell-updates
+  config.parity   the result of the timed solve against the reference run's golden (tests/golden/mode1_64x64.npz):
+               CG stopping iterations, error trace, deformation bits on the stored lattice; at N > 1 additionally
+               against the single-GPU record (tests/golden/bench_n1_record.json)
+  config.res128   the north-star configuration (128^4, BASELINE.json configs[4]) measured in the same process:
+               1 warm-up + 2 solves, value / cg_iters / final_error / dominant kernel
+--impl reference times the reference's CPU implementation on the SAME configuration (one real solve, unscaled).
 """
 import argparse
 import ctypes as C
@@ -121,63 +127,90 @@ def cpu_reference_solve(res, threads=None):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU path, all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation (all host threads) on the benchmarked configuration.
+    One REAL solve at `--res` (64^4: several minutes), no scaling; --steps/--warmup are not honoured beyond that -- a
+    CPU solve has no clocks to settle and K = 20 of them would take hours -- and the line says so (steps 1, warmup 0).
+    Only 128^4 (hours, > 90 GB) is extrapolated from the measured 64^4 solve by cell count and labelled as such."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample_res = 32 if args.res >= 64 else max(16, args.res // 2)
+    sample_res = min(args.res, 64)
     scale = (args.res / sample_res) ** 4
-    times = []
-    kind = cores = None
-    for s in range(args.warmup + args.steps):
-        if s < args.warmup and s > 0:
-            continue  # one warm-up solve is enough to page the library in; CPU timing has no clocks to settle
-        sec, kind, cores = cpu_reference_solve(sample_res)
-        if s >= args.warmup:
-            times.append(sec)
-    sec = float(np.mean(times)) * scale
-    sample = ("%s CPU implementation, full mode-1 solve on the %d^4 synthetic two-drop pair (1/%d of the cells of the "
-              "%d^4 workload), wall time scaled x%d by cell count" % (kind, sample_res, int(scale), args.res, int(scale)))
-    line = {"metric": METRIC, "value": sec, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    sec, kind, cores = cpu_reference_solve(sample_res)
+    if scale == 1:
+        sample = ("%s CPU implementation (OpenMP build, %d threads), ONE full mode-1 solve on the %d^4 synthetic two-drop pair: "
+                  "the benchmarked configuration itself, measured, not scaled" % (kind, cores, args.res))
+    else:
+        sample = ("%s CPU implementation (%d threads), one full mode-1 solve on the %d^4 synthetic pair measured (%.1f s), "
+                  "EXTRAPOLATED x%d by cell count to %d^4" % (kind, cores, sample_res, sec, int(scale), args.res))
+    sec *= scale
+    line = {"metric": METRIC, "value": sec, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+            "requested": {"steps": args.steps, "warmup": args.warmup},
             "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "flof mode 1 (opticalFlowMultiscale4d, README parameters) on synthetic two-drop "
-                                   "4D SDF pair %d^4" % args.res, "res": args.res},
+            "config": workload_config(args.res, 1, reference=True),
             "cpu_baseline": {"value": sec, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--res", type=int, default=64)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+def workload_config(res, world, reference=False):
+    cells = res ** 4
+    cfg = {"workload": "flof mode 1 (opticalFlowMultiscale4d, README parameters: wSmooth 1e-3, wEnergy 1e-4, "
+                       "cgAccuracy 1e-2, postVelBlur 4, multiStep 3, minGridSize 20, final projection) on "
+                       "synthetic two-drop 4D SDF pair %d^4%s" % (res, {64: " (BASELINE.json configs[3])", 128: " (BASELINE.json configs[4])"}.get(res, "")),
+           "res": res, "levels": [res >> l for l in range(8) if (res >> l) > 10 and (l == 0 or (res >> (l - 1)) > 20)]}
+    if not reference:
+        cfg["l2"] = "working set (%d MB of grids) exceeds the 126 MB L2; no explicit flush" % (cells * 4 * 30 // 2 ** 20)
+        cfg["parallelism"] = ("1 GPU" if world == 1 else
+                              "t-sharded over %d GPUs (levels >= 2^22 cells; halos and CG scalars through NVLink peer "
+                              "mailboxes, NCCL all-gathers)" % world)
+    return cfg
 
-    if args.impl == "reference":
-        return run_reference_arm(args)
 
-    # rank 0 prints exactly one JSON line on stdout: NCCL writes its version banner / debug lines to fd 1, so
-    # stdout is pointed at stderr until the line is printed
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
+def bits_checksum(a):
+    """order-independent integer checksum of a float32 array's bit patterns (exactly reproducible, unlike an fp sum)"""
+    u = np.ascontiguousarray(a).view(np.uint32).ravel()
+    return "%016x-%08x" % (int(u.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(u)))
+
+
+N1_RECORD = os.path.join(ROOT, "tests", "golden", "bench_n1_record.json")
+
+
+def parity_record(res, vel_h, cg_iters, errs, world):
+    """What the timed solve produced, against the reference run's golden (64^4) and the committed single-GPU record."""
+    out = {"cg_iters": cg_iters, "final_error": errs[-1] if errs else None, "deformation_checksum": bits_checksum(vel_h)}
+    gfn = os.path.join(ROOT, "tests", "golden", "mode1_%dx%d.npz" % (res, res))
+    if os.path.isfile(gfn):
+        g = np.load(gfn)
+        st = int(g["stride"])
+        sub = vel_h.reshape(res, res, res, res, 4)[::st, ::st, ::st, ::st]
+        d = sub.astype(np.float64) - g["vel_sub"]
+        out["vs_reference_run"] = {
+            "golden": "tests/golden/mode1_%dx%d.npz (unmodified reference, tests/golden/make_golden.py)" % (res, res),
+            "cg_iters_equal": cg_iters == [int(x) for x in g["cg_iters"]],
+            "error_trace_equal_1e-6": bool(len(errs) == len(g["errs"]) and np.allclose(errs, g["errs"], rtol=1e-6)),
+            "deformation_bit_identical_on_lattice": bool(np.array_equal(sub, g["vel_sub"])),
+            "deformation_rel_l2": float(np.linalg.norm(d.ravel()) / max(np.linalg.norm(g["vel_sub"].astype(np.float64).ravel()), 1e-300)),
+            "deformation_max_abs_cells": float(np.abs(d).max())}
+    try:
+        rec = json.load(open(N1_RECORD)).get(str(res))
+    except Exception:
+        rec = None
+    if rec is not None:
+        out["parity_vs_n1"] = bool(rec["cg_iters"] == cg_iters and rec["deformation_checksum"] == out["deformation_checksum"])
+        out["n1_record"] = "tests/golden/bench_n1_record.json (single-GPU run of this bench)"
+    elif world == 1:
+        out["parity_vs_n1"] = True
+    return out
+
+
+def measure(ctx, api, fdist, res, steps, warmup, world, local_rank, with_e2e, prof_steps):
+    """Times `steps` mode-1 solves at res^4 (after `warmup`); returns a dict of everything the JSON line needs."""
     from ofblend_b200 import capi, synth
-    from ofblend_b200 import dist as fdist
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # one process per GPU; the NCCL communicator lives inside libflof_b200.so (ofblend_b200/dist.py)
-    ctx, rank, world = fdist.init()
-    api = capi.HostAPI(ctx)
-    res = args.res
     dims = (res, res, res, res)
     cells = res ** 4
-
     # inputs: synthetic two-drop pair, pre-processed on the GPU by the product kernels (outside the timed region)
     i0_h = synth.post_process(synth.two_drop_phi(dims, 0), api)
     i1_h = synth.post_process(synth.two_drop_phi(dims, 1), api)
@@ -194,7 +227,7 @@ def main():
         ctx.grid_set_const(vel, zero4)
         return ctx.optical_flow_multiscale4d(vel, i0, i1, params, want_trace=True)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_step()
 
     sampler = ClockSampler(local_rank)
@@ -206,7 +239,7 @@ def main():
     cg_ms = 0.0
     cg_updates = 0
     trace = None
-    for _ in range(args.steps):
+    for _ in range(steps):
         err, trace = one_step()
         dev_ms += trace.total_ms
         n = min(trace.n_solves, 64)
@@ -215,40 +248,55 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     launches = ctx.launches - launches0
-
+    out = {"res": res, "cells": cells}
     # device time (CUDA events on the library's stream, recorded inside the call); max over ranks
-    ms_per_step = fdist.max_over_ranks(ctx, dev_ms / args.steps)
+    out["ms_per_step"] = fdist.max_over_ranks(ctx, dev_ms / steps)
+    out["wall_ms_per_step"] = wall / steps * 1e3
+    out["launches"] = int(launches)
+    out["cg_cell_updates_per_s"] = cg_updates / max(cg_ms * 1e-3, 1e-12)
+    out["cg_updates_per_step"] = cg_updates / steps
+    out["cg_iters"] = [int(trace.cg_iters[q]) for q in range(min(trace.n_solves, 64))]
+    out["cg_cells"] = [int(trace.cg_cells[q]) for q in range(min(trace.n_solves, 64))]
+    out["errs"] = [float(trace.errs[q]) for q in range(min(trace.n_errs, 64))]
+    out["seq"] = ctx.seq_stats()
+    # what the timed solve produced, checked on the host (outside every timed region)
+    out["parity"] = parity_record(res, vel.download(), out["cg_iters"], out["errs"], world)
 
     # ---- e2e: host buffers through the plugin-level C-ABI call, copies inside the timed region
-    hb = {}
-    for name, nbytes in (("i0", cells * 4), ("i1", cells * 4), ("vel", cells * 16)):
-        p = C.c_void_p()
-        ctx._chk(ctx.lib.flof_host_alloc(ctx.h, C.byref(p), C.c_size_t(nbytes)))
-        hb[name] = (p, np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(nbytes // 4,)))
-    hb["i0"][1][:] = i0_h.ravel()
-    hb["i1"][1][:] = i1_h.ravel()
-    e2e_times = []
-    tr2 = capi.MultiscaleTrace()
-    e2 = C.c_float(0)
-    for s in range(1 + args.steps):
-        hb["vel"][1][:] = 0.0
-        barrier()
-        t1 = time.perf_counter()
-        ctx._chk(ctx.lib.flof_optical_flow_multiscale4d_host(ctx.h, hb["vel"][0], hb["i0"][0], hb["i1"][0],
-                                                             capi.Dim4(*dims), C.byref(params), C.byref(tr2), C.byref(e2)))
-        result_norm = float(hb["vel"][1][:4096].sum())  # touch the result on the host
-        barrier()
-        if s > 0:
-            e2e_times.append(time.perf_counter() - t1)
-    e2e_s = fdist.max_over_ranks(ctx, float(np.mean(e2e_times)))
+    if with_e2e:
+        hb = {}
+        for name, nbytes in (("i0", cells * 4), ("i1", cells * 4), ("vel", cells * 16)):
+            p = C.c_void_p()
+            ctx._chk(ctx.lib.flof_host_alloc(ctx.h, C.byref(p), C.c_size_t(nbytes)))
+            hb[name] = (p, np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(nbytes // 4,)))
+        hb["i0"][1][:] = i0_h.ravel()
+        hb["i1"][1][:] = i1_h.ravel()
+        e2e_times = []
+        tr2 = capi.MultiscaleTrace()
+        e2 = C.c_float(0)
+        for s in range(1 + steps):
+            hb["vel"][1][:] = 0.0
+            barrier()
+            t1 = time.perf_counter()
+            ctx._chk(ctx.lib.flof_optical_flow_multiscale4d_host(ctx.h, hb["vel"][0], hb["i0"][0], hb["i1"][0],
+                                                                 capi.Dim4(*dims), C.byref(params), C.byref(tr2), C.byref(e2)))
+            float(hb["vel"][1][:4096].sum())  # touch the result on the host
+            barrier()
+            if s > 0:
+                e2e_times.append(time.perf_counter() - t1)
+        out["e2e_s"] = fdist.max_over_ranks(ctx, float(np.mean(e2e_times)))
+        # the e2e call must deliver the same bits as the resident call (it is the same solve behind host copies)
+        out["parity"]["e2e_result_equals_resident"] = bool(bits_checksum(hb["vel"][1]) == out["parity"]["deformation_checksum"])
+        for name in hb:
+            ctx.lib.flof_host_free(ctx.h, hb[name][0])
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    out["clocks"] = sampler.summary()
 
     # ---- live per-kernel timing: CUDA events bracket every launch of K more steps of the same workload
     # (kept out of the steps timed above so the ~2 event records per launch do not perturb `value`)
     stats = (KernelStat * 256)()
     nstat = C.c_int(0)
-    prof_steps = max(1, min(args.steps, 3))
     ctx._chk(ctx.lib.flof_profile_begin(ctx.h))
     for _ in range(prof_steps):
         one_step()
@@ -270,60 +318,164 @@ def main():
             row["gbs"] = row["bytes_per_launch"] / (row["avg_launch_ms"] * 1e-3) / 1e9
             row["frac"] = row["gbs"] / peak
         ktab.append(row)
+    out["kernels"] = ktab
+    out["peak"], out["peak_src"] = peak, peak_src
+    out["prof_steps"] = prof_steps
+    # step-level roofline: algorithmic bytes of all classified launches / step time / peak
+    alg = sum(r["bytes_per_launch"] * r["launches_per_step"] for r in ktab if "bytes_per_launch" in r)
+    out["step_roofline_frac"] = alg / (out["ms_per_step"] * 1e-3) / 1e9 / peak
+    for g in (i0, i1, vel):
+        g.free()
+    return out
+
+
+def roofline_of(m):
+    ktab = m["kernels"]
     dom = next((r for r in ktab if "gbs" in r), None)  # ktab is sorted by total time: dominant (kernel, level)
-    if dom is not None:
-        # measured DRAM traffic of that kernel: one `ncu --set full` capture per round (profiles/r1_ncu_traffic.json),
-        # per cell, scaled to the cells of this launch
-        traffic, traffic_src = None, None
+    if dom is None:
+        return {"bound": "hbm", "achieved": None, "peak": m["peak"], "unit": "GB/s", "frac": None, "traffic": None}
+    # measured DRAM traffic of that kernel: one `ncu --set full` capture per round (profiles/*_ncu_traffic.json),
+    # per cell, scaled to the cells of this launch
+    traffic, traffic_src = None, None
+    for fn in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
             tk = next((k for k in tj["kernels"] if dom["kernel"].startswith(k)), None)
             if tk is not None:
                 traffic = tj["kernels"][tk]["bytes_per_cell"] * dom["cells_per_launch"]
-                traffic_src = "profiles/r1_ncu_traffic.json (ncu --set full at 64^4, %.1f B/cell)" % tj["kernels"][tk]["bytes_per_cell"]
+                traffic_src = "profiles/%s (ncu --set full at 64^4, %.1f B/cell%s)" % (
+                    fn, tj["kernels"][tk]["bytes_per_cell"], ", captured at commit %s" % tj["commit"] if "commit" in tj else "")
+                break
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": dom["kernel"], "cells_per_launch": dom["cells_per_launch"], "achieved": dom["gbs"],
-                    "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": peak_src,
-                    "bytes_per_launch": dom["bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
-                    "share_of_step": dom["share"],
-                    "how": "CUDA events around every launch on the library stream, %d steps" % prof_steps}
-    else:
-        roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
+    return {"bound": "hbm", "kernel": dom["kernel"], "cells_per_launch": dom["cells_per_launch"], "achieved": dom["gbs"],
+            "peak": m["peak"], "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": m["peak_src"], "bytes_per_launch": dom["bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
+            "share_of_step": dom["share"], "step_frac": m["step_roofline_frac"],
+            "how": "CUDA events around every launch on the library stream, %d steps" % m["prof_steps"]}
 
-    line = {"metric": METRIC, "value": ms_per_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
+
+def cpu_baseline_sample(res, gpu_updates_per_step, api):
+    """cpu_baseline: the reference's opticalFlow4d (assembly + Jacobi-PCG, ref optflow4d.cpp:361-553) on the finest level of
+    the benchmarked pair -- the first solve of the mode-1 run, without the blur -- timed on the host cores, then scaled to
+    the whole solve by CG cell-updates (the reference's assembly and CG are single-threaded whatever the build)."""
+    from oracle import ref
+    from ofblend_b200 import synth
+    if ref.available():
+        mod, kind = ref, "reference"
+    else:
+        from oracle import port as mod
+        kind = "port"
+    cores = mod.set_threads(os.cpu_count() or 1)
+    dims = (res, res, res, res)
+    i0 = synth.post_process(synth.two_drop_phi(dims, 0), api)   # same inputs as the GPU run (bit-identical pre-processing)
+    i1 = synth.post_process(synth.two_drop_phi(dims, 1), api)
+    v0 = np.zeros(i0.shape + (4,), np.float32)
+    acc = 1e-1  # a loose CG accuracy bounds the sample to ~10-20 s; the per-iteration cost does not depend on it
+    # the iteration count comes from the product's own run of the same call (bit-identical CG: same stopping iteration)
+    _, it = api.optical_flow4d(v0, i0, i1, 1e-3, 1e-4, 0., acc, 0.1, want_iters=True)
+    t0 = time.time()
+    mod.optical_flow4d(v0, i0, i1, 1e-3, 1e-4, 0., acc, 0.1)
+    sec = time.time() - t0
+    upd = max(int(it), 1) * res ** 4
+    scaled = sec * gpu_updates_per_step / upd
+    return {"value": scaled, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample_seconds": sec, "sample_cg_iterations": int(it), "cpu_cg_cell_updates_per_s": upd / sec,
+            "sample": "%s CPU implementation: opticalFlow4d(wSmooth 1e-3, wEnergy 1e-4, postVelBlur 0, cgAccuracy %.0e) on the "
+                      "%d^4 level of the benchmarked pair = assembly + %d CG iterations, %.1f s measured; scaled to the "
+                      "full solve by CG cell-updates (x%.1f; blur / projection / advection of the CPU path NOT included, "
+                      "so this under-states the CPU time -- the reference arm measures the whole solve)"
+                      % (kind, acc, res, int(it), sec, gpu_updates_per_step / upd)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--res", type=int, default=64)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-res128", action="store_true", help="skip the 128^4 sub-record (config.res128)")
+    ap.add_argument("--write-n1-record", action="store_true", help="store this run's result as the single-GPU parity record")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    # rank 0 prints exactly one JSON line on stdout: NCCL writes its version banner / debug lines to fd 1, so
+    # stdout is pointed at stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    from ofblend_b200 import capi
+    from ofblend_b200 import dist as fdist
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # one process per GPU; the NCCL communicator lives inside libflof_b200.so (ofblend_b200/dist.py)
+    ctx, rank, world = fdist.init()
+    api = capi.HostAPI(ctx)
+    res = args.res
+    cells = res ** 4
+
+    m = measure(ctx, api, fdist, res, args.steps, args.warmup, world, local_rank, True, max(1, min(args.steps, 3)))
+    config = workload_config(res, world)
+    config["parity"] = m["parity"]
+    config["parity_vs_n1"] = m["parity"].get("parity_vs_n1")
+    config["seq_dot_stats"] = m["seq"]
+
+    if res == 64 and not args.no_res128:
+        # the north-star configuration in the same process (1 warm-up + 2 solves; BASELINE.json configs[4])
+        try:
+            m2 = measure(ctx, api, fdist, 128, 2, 1, world, local_rank, False, 1)
+            dom2 = roofline_of(m2)
+            config["res128"] = {"value": m2["ms_per_step"] / 1e3, "unit": UNIT, "steps": 2, "warmup": 1,
+                                "cg_iters": m2["cg_iters"], "final_error": m2["errs"][-1] if m2["errs"] else None,
+                                "cg_cell_updates_per_s": m2["cg_cell_updates_per_s"],
+                                "deformation_checksum": m2["parity"]["deformation_checksum"],
+                                "parity_vs_n1": m2["parity"].get("parity_vs_n1"),
+                                "dominant_kernel": {k: dom2.get(k) for k in ("kernel", "frac", "avg_launch_ms", "share_of_step")},
+                                "step_roofline_frac": m2["step_roofline_frac"],
+                                "kernels": [{k: r.get(k) for k in ("kernel", "cells", "launches_per_step", "avg_launch_ms", "share", "frac")}
+                                            for r in m2["kernels"][:10]]}
+        except Exception as e:  # noqa: BLE001
+            config["res128"] = {"error": str(e)[:300]}
+            m2 = None
+    else:
+        m2 = None
+
+    line = {"metric": METRIC, "value": m["ms_per_step"] / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "flof mode 1 (opticalFlowMultiscale4d, README parameters: wSmooth 1e-3, wEnergy 1e-4, "
-                                   "cgAccuracy 1e-2, postVelBlur 4, multiStep 3, minGridSize 20, final projection) on "
-                                   "synthetic two-drop 4D SDF pair %d^4%s" % (res, {64: " (BASELINE.json configs[3])", 128: " (BASELINE.json configs[4])"}.get(res, "")),
-                       "res": res, "levels": [res >> l for l in range(8) if (res >> l) > 10 and (l == 0 or (res >> (l - 1)) > 20)],
-                       "l2": "working set (%d MB of grids) exceeds the 126 MB L2; no explicit flush" % (cells * 4 * 30 // 2 ** 20),
-                       "parallelism": "1 GPU" if world == 1 else "t-sharded over %d GPUs (levels >= 2^22 cells; halos and CG scalars through NVLink peer mailboxes, NCCL all-gathers)" % world},
-            "wall_ms_per_step": wall / args.steps * 1e3,
-            "cg_cell_updates_per_s": cg_updates / max(cg_ms * 1e-3, 1e-12),
-            "cg_iters": [int(trace.cg_iters[q]) for q in range(min(trace.n_solves, 64))],
-            "final_error": float(trace.errs[min(trace.n_errs, 64) - 1]) if trace.n_errs else None,
-            "gpu_launches": int(launches),
+            "config": config,
+            "wall_ms_per_step": m["wall_ms_per_step"],
+            "cg_cell_updates_per_s": m["cg_cell_updates_per_s"],
+            "cg_iters": m["cg_iters"],
+            "final_error": m["errs"][-1] if m["errs"] else None,
+            "gpu_launches": m["launches"],
             # every rank uploads the (replicated) inputs and downloads the complete deformation: whole-job bytes
-            "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": cells * 24 * world, "d2h_bytes_per_step": cells * 16 * world,
+            "e2e": {"value": m["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": cells * 24 * world, "d2h_bytes_per_step": cells * 16 * world,
                     "bytes_per_rank": {"h2d": cells * 24, "d2h": cells * 16},
                     "api": "flof_optical_flow_multiscale4d_host (pinned host buffers)"},
-            "clocks": sampler.summary(),
-            "roofline": roofline,
-            "kernels": ktab[:14]}
+            "clocks": m["clocks"],
+            "roofline": roofline_of(m),
+            "kernels": m["kernels"][:16]}
     if rank == 0:
+        if args.write_n1_record and world == 1:
+            try:
+                rec = json.load(open(N1_RECORD))
+            except Exception:
+                rec = {}
+            for mm in (m, m2):
+                if mm is not None:
+                    rec[str(mm["res"])] = {"cg_iters": mm["cg_iters"], "final_error": mm["errs"][-1],
+                                           "deformation_checksum": mm["parity"]["deformation_checksum"]}
+            json.dump(rec, open(N1_RECORD, "w"), indent=1)
         if not args.no_cpu_baseline and world == 1:
-            sample_res = 32 if res >= 64 else max(16, res // 2)
-            sec, kind, cores = cpu_reference_solve(sample_res)
-            scale = (res / sample_res) ** 4
-            line["cpu_baseline"] = {"value": sec * scale, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": "%s CPU implementation, one full mode-1 solve on the %d^4 synthetic pair "
-                                              "(%.1f s measured), scaled x%d by cell count to %d^4"
-                                              % (kind, sample_res, sec, int(scale), res)}
+            line["cpu_baseline"] = cpu_baseline_sample(res if res <= 64 else 64, m["cg_updates_per_step"], api)
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    barrier()
+    barrier_all = fdist.barrier
+    barrier_all(ctx)
     ctx.close()
     return 0
 

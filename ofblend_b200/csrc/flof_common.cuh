@@ -19,6 +19,7 @@
 // device scratch for deterministic two-stage reductions ("last block finishes")
 struct flof_reduce_scratch {
 	double dsum[3][FLOF_MAX_PARTIALS];  // partial fp64 sums, three independent slots
+	double asum[FLOF_MAX_PARTIALS];     // partial sums of |product| (sequential-order dot products, flof_seqsum.cuh)
 	float fmax[FLOF_MAX_PARTIALS];
 	float fmin[FLOF_MAX_PARTIALS];
 	unsigned int counter[4];            // arrival counters (self-resetting)

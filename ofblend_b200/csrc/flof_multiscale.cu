@@ -306,6 +306,9 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 		} else {
 			DevBuf velTmp2(ctx);
 			MS_RET(velTmp2.alloc(vb, true));
+			// the projection gathers phiOrg at back-traced positions that leave this rank's slab: complete i0warped first
+			// (after the pre-warp it is valid on the own slices only)
+			MS_RET(flof_allgather_slabs(ctx, i0warped.p, d.nt, sizeof(float) * (size_t)d.nx * d.ny * d.nz));
 			MS_RET(flof_corr_vels_of4d(ctx, velCurr.f(), velTmp2.f(), i0warped.f(), i1, d, projMaxDist, P.postVelBlur,
 			                           P.resetBndWidth, (int)projMaxIter));
 			MS_RET(flof_grid_binary(ctx, vel, velTmp2.f(), n, 4, FLOF_OP_ADD));

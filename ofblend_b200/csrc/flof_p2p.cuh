@@ -29,7 +29,9 @@ __device__ __forceinline__ size_t mbox_buf_off(size_t cap, int from, unsigned in
 // all-reduce of n <= 4 doubles held in shared vals[] (called by every thread of ONE block with >= nranks threads;
 // result in vals[], valid for every thread after the call).  vals[0..nsum) are summed in rank order -- the same
 // order on every rank, so all ranks get the identical bits and stay in lock step --, the rest max (or min).
-__device__ __forceinline__ void p2p_allreduce_block(const flof_p2p_dev &pp, double *vals, int n, int nsum, bool use_min)
+// excl (optional, shared, >= nsum doubles): the sum over the LOWER ranks only (exclusive prefix in rank order).
+__device__ __forceinline__ void p2p_allreduce_block(const flof_p2p_dev &pp, double *vals, int n, int nsum, bool use_min,
+                                                    double *excl = NULL)
 {
 	// the sequence number lives on the device and advances only when an all-reduce really runs (the CG kernels
 	// return early once the solve is done), so consecutive exchanges always alternate the mailbox parity
@@ -51,7 +53,9 @@ __device__ __forceinline__ void p2p_allreduce_block(const flof_p2p_dev &pp, doub
 	if (j == 0) {
 		for (int q = 0; q < n; ++q) {
 			double acc = ((volatile double *)me->ar[par][0].v)[q];
+			if (excl && q < nsum) excl[q] = 0.;
 			for (int r = 1; r < pp.nranks; ++r) {
+				if (excl && q < nsum && r == pp.rank) excl[q] = acc;
 				const double x = ((volatile double *)me->ar[par][r].v)[q];
 				acc = q < nsum ? acc + x : (use_min ? fmin(acc, x) : fmax(acc, x));
 			}

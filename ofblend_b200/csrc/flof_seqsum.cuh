@@ -1,40 +1,86 @@
 // flof_seqsum.cuh -- device state of the sequential-order dot products (see flof_seqsum_core.h for the arithmetic,
-// flof_seqsum.cu for the kernels).  ref: dotProd optflow4d.cpp:234-241.
+// flof_seqsum_kernels.cuh for the kernels).  ref: dotProd optflow4d.cpp:234-241.
+//
+// Organisation (two passes, no spinning, identical on one GPU and on a t-sharded level):
+//   pass 1  the kernel that PRODUCES the vectors (k_cg_init / k_cg_apply / k_cg_update; k_seq_agg for the stand-alone
+//           entry) walks the cells in contiguous SEGMENTS, one CTA per segment, and leaves per segment an approximate
+//           sum of its products and an upper bound of the sum of their magnitudes; its "last block" tail turns them into
+//           exclusive prefixes (seq_seg) -- on a sharded level after the in-kernel all-reduce, which also yields the
+//           lower ranks' share.
+//   pass 2  k_dot_seq re-reads the two vectors (32 B/cell).  With the approximate prefix known, a segment whose running sum
+//           provably stays inside one binade is folded into ONE rounding function by eight independent warps (no block
+//           barrier); the few segments around a binade crossing (or where the sum still builds up from zero) take the
+//           careful path: leaf by leaf, leaves that are still unsafe product by product (runs + raw products).
+//   resolve k_seq_resolve (one CTA): composes the segment entries in parallel, then one thread walks runs and raw products
+//           with real fp64 adds.  On a sharded level the exact running sum travels rank 0 -> 1 -> ... through the peer
+//           mailboxes and the last rank broadcasts the total.
 #pragma once
 #include "flof_common.cuh"
 #include "flof_seqsum_core.h"
 
-#define SEQ_U 4                          // cells per thread and leaf
+#define SEQ_U 4                              // cells per thread and leaf
 #define SEQ_LEAF_CELLS (FLOF_BLOCK * SEQ_U)  // 1024 cells = 4096 products per leaf
-#define SEQ_DMAX 1024                    // dirty leaves the resolver can take per dot product
-#define SEQ_POOL (1 << 18)               // pieces (32 B each) all dirty leaves of one dot product may use
-#define SEQ_PIECE_SMEM 1024              // pieces the resolver stages in shared memory
+#define SEQ_CHUNK_CELLS 128                  // fast path: cells a warp folds per step (4 per lane)
+#define SEQ_ECAP 64                          // entries a segment may emit (fast path: 1)
+#define SEQ_DMAX 1024                        // dirty leaves the resolver can take per dot product
+#define SEQ_POOL (1 << 18)                   // pieces (32 B each) all dirty leaves of one dot product may use
+#define SEQ_PIECE_SMEM 1024                  // pieces the resolver stages in shared memory
+#define SEQ_EMAX 3072                        // segment entries the resolver stages in shared memory
+#define SEQ_PLAIN_MAX (1 << 21)                // cells up to which the resolver's fallback is the plain one-thread loop
+#define SEQ_SA_SLACK 1.001                   // the producers sum |product| in fp32: inflate to a rigorous upper bound
 
-// decoupled look-back descriptor of one leaf: approximate sum / sum of magnitudes of the leaf (agg) and of
-// everything up to and including it (pre).  A part is valid when its stamp equals the epoch of the launch.
-struct seq_desc {
-	unsigned int st_agg, st_pre;
-	double ax, aa, px, pa;
-	double pad;
+// contiguous decomposition of one rank's cell range into segments (the same for the producing kernel and k_dot_seq)
+struct seq_part {
+	int ncells;     // cells of the range
+	int seg_cells;  // cells per segment, a multiple of SEQ_LEAF_CELLS
+	int nseg;       // <= FLOF_MAX_PARTIALS
+};
+
+struct seq_seg {  // per segment: approximate sum / magnitude bound of the segment and of everything before it in the range
+	double sx, sa, px, pa;
 };
 
 struct seq_ctl {  // device-resident control block of one context
-	unsigned int ticket;       // next leaf to hand out (reset by the resolver)
 	unsigned int ndirty;       // dirty leaves of the running dot product
 	unsigned int pool_used;    // pieces allocated from the pool
 	unsigned int flags;        // bit 0: non-finite product seen, bit 1: capacity exceeded, bit 2: consistency check failed
+	unsigned int pad;
 	double result;             // last resolved sum (exact bits of the sequential loop)
-	unsigned long long n_dots, n_dirty, n_raw, n_pieces, n_fallback, n_inconsistent;  // statistics since context creation
-	int dirty_leaf[SEQ_DMAX];
-	unsigned int dirty_base[SEQ_DMAX];
-	unsigned int dirty_cnt[SEQ_DMAX];
+	double tot[2];             // approximate sum / magnitude bound of this rank's range (tail of pass 1)
+	double off[2];             // the same for all lower ranks together (0 on a single GPU)
+	unsigned long long n_dots, n_dirty, n_raw, n_pieces, n_fallback, n_inconsistent, n_slow_segments, n_inexact;  // statistics since context creation
 };
 
 struct flof_seq {  // host-side handle (ctx->seq)
-	seq_desc *desc;
-	seq_rec *leaf;
-	seq_rec *pool;
+	seq_seg *seg;      // [FLOF_MAX_PARTIALS]
+	seq_rec *ent;      // [FLOF_MAX_PARTIALS * SEQ_ECAP] entries of the segments, in order
+	int *ecnt;         // [FLOF_MAX_PARTIALS]
+	double *aggx, *agga;  // [FLOF_MAX_PARTIALS] each: segment accumulators of the stencil kernel (atomics)
+	seq_rec *pool;     // [SEQ_POOL]
 	seq_ctl *ctl;
-	int64_t cap_leaves;
-	unsigned int epoch;
 };
+
+// host: segment size for a range of `ncells` cells; slice_cells = cells of one t-slice (0 if unknown).  A segment count
+// near per_sm CTAs per SM (the occupancy of the stencil kernel) keeps every producing CTA resident at once; segments that tile a t-slice make the t-1 / t+1
+// neighbours of the stencil kernel the CENTRE cells of another resident CTA at the same moment (synchronised streaming).
+static inline seq_part seq_make_part(int64_t ncells, int64_t slice_cells, int sm_count, int per_sm = 8)
+{
+	seq_part p;
+	const int64_t leaves = (ncells + SEQ_LEAF_CELLS - 1) / SEQ_LEAF_CELLS;
+	int64_t cap = (int64_t)sm_count * per_sm;
+	if (cap > FLOF_MAX_PARTIALS) cap = FLOF_MAX_PARTIALS;
+	int64_t R = (leaves + cap - 1) / cap;
+	if (R < 1) R = 1;
+	if (slice_cells > 0 && slice_cells % SEQ_LEAF_CELLS == 0) {
+		const int64_t lps = slice_cells / SEQ_LEAF_CELLS;
+		for (int64_t r = R; r <= 2 * R && r <= lps; ++r)
+			if (lps % r == 0) {
+				R = r;
+				break;
+			}
+	}
+	p.ncells = (int)ncells;
+	p.seg_cells = (int)(R * SEQ_LEAF_CELLS);
+	p.nseg = (int)((leaves + R - 1) / R);
+	return p;
+}

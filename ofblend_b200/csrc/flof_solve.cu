@@ -8,7 +8,9 @@
 // with the reference's fp32 operation order, so every matrix entry has the identical fp32 value.
 // Unknown layout = Vec4 AoS (idx = cell*4 + d, ref :60-64), i.e. one 128-bit access per cell.
 //
-// One CG iteration = three flat kernels over the cells (224 B/cell/iteration):
+// One CG iteration = three streaming kernels over the cells (224 B/cell/iteration), each CTA walking one
+// contiguous SEGMENT of the cell range (seq_make_part: all CTAs resident, segments tile the t-slices so that the t-1 / t+1
+// stencil neighbours are the centre cells of another resident CTA at the same moment):
 //   A: tmp = A*srch                       (+ partial fp64 dot(srch,tmp))
 //   B: result += alpha*srch; res -= alpha*tmp   (+ partial signed max(res), fp64 dot(res*precond,res))
 //   C: srch = res*precond + beta*srch     (the stop test and the state advance ran in the tail of B)
@@ -164,66 +166,6 @@ __device__ __forceinline__ void cg_init_finalize(flof_cg_state *st, double s, fl
 	}
 }
 
-// res = rhs, result = 0, tmp = res*precond, srch = tmp; residual0 = max(res), sigma = tmp.res
-__global__ void __launch_bounds__(FLOF_BLOCK)
-    k_cg_init(float4 *__restrict__ x, float4 *__restrict__ res, float4 *__restrict__ srch,
-              const float4 *__restrict__ grad, const float4 *__restrict__ rhs, int64_t cells, float diag,
-              float accuracy, int multi, int defer, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
-{
-	__shared__ double shd[32];
-	__shared__ float shf[32];
-	__shared__ double s_ar[4];
-	double dsum = 0.;
-	float mx = -3.402823466e+38f;
-	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
-		const float4 g = __ldg(grad + c), r = __ldg(rhs + c);
-		const float4 pc = precond_of(g, diag);
-		const float4 z = make_float4(r.x * pc.x, r.y * pc.y, r.z * pc.z, r.w * pc.w);
-		x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-		res[c] = r;
-		srch[c] = z;
-		dsum += dot4(z, r);
-		mx = fmaxf(mx, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
-	}
-	dsum = flof_block_sum(dsum, shd);
-	mx = flof_block_max(mx, shf);
-	if (threadIdx.x == 0) {
-		red->dsum[0][blockIdx.x] = dsum;
-		red->fmax[blockIdx.x] = mx;
-	}
-	if (flof_last_block(&red->counter[1])) {
-		double s = 0.;
-		float m = -3.402823466e+38f;
-		for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-			s += red->dsum[0][b];
-			m = fmaxf(m, red->fmax[b]);
-		}
-		s = flof_block_sum(s, shd);
-		m = flof_block_max(m, shf);
-		if (multi == 2) {  // sharded, peer mailboxes: combine the slabs of all ranks right here
-			if (threadIdx.x == 0) {
-				s_ar[0] = s;
-				s_ar[1] = (double)m;
-			}
-			p2p_allreduce_block(pp, s_ar, 2, 1, false);
-			s = s_ar[0];
-			m = (float)s_ar[1];
-		}
-		if (threadIdx.x == 0) {
-			if (multi == 1 || defer) {
-				// multi == 1: raw slab results; the ranks are combined by NCCL, then k_cg_init_finalize runs
-				// defer: sigma comes from the sequential-order dot product (k_seq_resolve finalizes the state)
-				st->sigmaNew = s;
-				st->residual = m;
-				st->done = 0;
-			} else {
-				cg_init_finalize(st, s, m, accuracy);
-			}
-		}
-	}
-}
-__global__ void k_cg_init_finalize(float accuracy, flof_cg_state *st) { cg_init_finalize(st, st->sigmaNew, st->residual, accuracy); }
 // end of an iteration's reductions (ref :311-317, 324): relative residual, stop test, sigma ring.  Runs in the tail
 // of k_cg_update (one thread, after every block has read the state) -- or as its own launch after the NCCL calls.
 __device__ __forceinline__ void cg_advance(flof_cg_state *st, double sigmaNew, float residual, int maxIter)
@@ -241,88 +183,234 @@ __device__ __forceinline__ void cg_advance(flof_cg_state *st, double sigmaNew, f
 	st->sigma[(it + 1) & 1] = sigmaNew;
 	if (it + 1 >= maxIter) st->done = 1;  // ref: loop bound cgMaxIter, returns false
 }
+
+// fp32 products accumulated in double like dot4; af additionally collects their magnitudes (fp32, an upper bound after
+// SEQ_SA_SLACK) for the error margin of the sequential-order dot products
+__device__ __forceinline__ double dot4a(const float4 &a, const float4 &b, float &af)
+{
+	float q = a.x * b.x;
+	double s = (double)q;
+	af += fabsf(q);
+	q = a.y * b.y;
+	s += (double)q;
+	af += fabsf(q);
+	q = a.z * b.z;
+	s += (double)q;
+	af += fabsf(q);
+	q = a.w * b.w;
+	s += (double)q;
+	af += fabsf(q);
+	return s;
+}
+
+#include "flof_seqsum_kernels.cuh"
+
+// what the reducing CG kernels need for the sequential-order dot products (pass 1, flof_seqsum.cuh)
+struct cg_seq {
+	int on;        // 1: leave per-segment prefixes for k_dot_seq and let k_seq_resolve advance the CG state
+	seq_seg *seg;
+	seq_ctl *ctl;
+	double *aggx, *agga;  // per-segment accumulators of the stencil kernel (atomics; zero between launches)
+};
+// tail of a reducing kernel in sequential-order mode (ONE block, every thread): per-segment prefixes, on a sharded
+// level the all-reduce that also yields the lower ranks' share; m: the block's max (thread 0), returned all-reduced
+__device__ __forceinline__ float cg_seq_tail(const cg_seq &sq, const seq_part &part, const double *px, const double *pa, float m,
+                                             bool with_max, int multi, const flof_p2p_dev &pp, double *shd, double *s_ar)
+{
+	double tx, ta;
+	seq_tail_scan(sq.seg, part.nseg, px, pa, shd, tx, ta);
+	double ox = 0., oa = 0.;
+	if (multi == 2) {
+		if (threadIdx.x == 0) {
+			s_ar[0] = tx;
+			s_ar[1] = ta;
+			s_ar[2] = (double)m;
+		}
+		p2p_allreduce_block(pp, s_ar, with_max ? 3 : 2, 2, false, s_ar + 4);
+		if (with_max) m = (float)s_ar[2];
+		ox = s_ar[4];
+		oa = s_ar[5];
+	}
+	if (threadIdx.x == 0) {
+		sq.ctl->tot[0] = tx;
+		sq.ctl->tot[1] = ta;
+		sq.ctl->off[0] = ox;
+		sq.ctl->off[1] = oa;
+	}
+	return m;
+}
+
+// res = rhs, result = 0, tmp = res*precond, srch = tmp; residual0 = max(res), sigma = tmp.res
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_cg_init(float4 *__restrict__ x, float4 *__restrict__ res, float4 *__restrict__ srch,
+              const float4 *__restrict__ grad, const float4 *__restrict__ rhs, seq_part part, float diag,
+              float accuracy, int multi, cg_seq sq, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
+{
+	__shared__ double shd[32];
+	__shared__ float shf[32];
+	__shared__ double s_ar[8];
+	double dsum = 0.;
+	float af = 0.f;
+	float mx = -3.402823466e+38f;
+	const int c0 = (int)blockIdx.x * part.seg_cells, c1 = min(c0 + part.seg_cells, part.ncells);
+	for (int c = c0 + (int)threadIdx.x; c < c1; c += FLOF_BLOCK) {
+		const float4 g = __ldg(grad + c), r = __ldg(rhs + c);
+		const float4 pc = precond_of(g, diag);
+		const float4 z = make_float4(r.x * pc.x, r.y * pc.y, r.z * pc.z, r.w * pc.w);
+		x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+		res[c] = r;
+		srch[c] = z;
+		dsum += dot4a(z, r, af);
+		mx = fmaxf(mx, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
+	}
+	double asum = (double)af;
+	seq_block_sum2(dsum, asum, shd);
+	mx = flof_block_max(mx, shf);
+	if (threadIdx.x == 0) {
+		red->dsum[0][blockIdx.x] = dsum;
+		red->asum[blockIdx.x] = asum;
+		red->fmax[blockIdx.x] = mx;
+	}
+	if (flof_last_block(&red->counter[1])) {
+		double s = 0.;
+		float m = -3.402823466e+38f;
+		for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+			s += red->dsum[0][b];
+			m = fmaxf(m, red->fmax[b]);
+		}
+		s = flof_block_sum(s, shd);
+		m = flof_block_max(m, shf);
+		if (sq.on) {
+			// sigma comes from the sequential-order dot product (k_seq_resolve finalizes the state)
+			m = cg_seq_tail(sq, part, red->dsum[0], red->asum, m, true, multi, pp, shd, s_ar);
+			if (threadIdx.x == 0) {
+				st->sigmaNew = s;
+				st->residual = m;
+				st->done = 0;
+			}
+			return;
+		}
+		if (multi == 2) {  // sharded, peer mailboxes: combine the slabs of all ranks right here
+			if (threadIdx.x == 0) {
+				s_ar[0] = s;
+				s_ar[1] = (double)m;
+			}
+			p2p_allreduce_block(pp, s_ar, 2, 1, false);
+			s = s_ar[0];
+			m = (float)s_ar[1];
+		}
+		if (threadIdx.x == 0) {
+			if (multi == 1) {
+				// raw slab results; the ranks are combined by NCCL, then k_cg_init_finalize runs
+				st->sigmaNew = s;
+				st->residual = m;
+				st->done = 0;
+			} else {
+				cg_init_finalize(st, s, m, accuracy);
+			}
+		}
+	}
+}
+__global__ void k_cg_init_finalize(float accuracy, flof_cg_state *st) { cg_init_finalize(st, st->sigmaNew, st->residual, accuracy); }
 __global__ void k_cg_update_finalize(int maxIter, flof_cg_state *st)
 {
 	if (st->done) return;
 	cg_advance(st, st->sigmaNew, st->residual, maxIter);
 }
 
-#include "flof_seqsum_kernels.cuh"
-
 // A: tmp = A * srch (ref applyMat :211-232), partial dot(srch, tmp)
-// TILED: the 256 cells a CTA handles per step form a compact 8 x 8 x 4 (x,y,z) brick instead of 256
-// consecutive cells of a row.  The six spatial neighbour loads of the brick then mostly hit L1 (the flat
-// traversal was L2->L1 bandwidth bound: ~112 B/cell from L2 for 48 B/cell of DRAM traffic, ncu profiles/r1);
-// a warp still reads four full 128-byte lines per load.  Needs nx%8 == ny%8 == nz%4 == 0.
-struct cg_tiles { int ntx, nty, ntz, nx, ny, nz; };
-__device__ __forceinline__ int64_t cg_tile_cell(const cg_tiles &q, int64_t w)
-{
-	const unsigned T = (unsigned)(w >> 8), tid = (unsigned)w & 255u;
-	const unsigned tx = T % q.ntx, r1 = T / q.ntx, ty = r1 % q.nty, r2 = r1 / q.nty, tz = r2 % q.ntz, tt = r2 / q.ntz;
-	const unsigned x = tx * 8 + (tid & 7), y = ty * 8 + ((tid >> 3) & 7), z = tz * 4 + (tid >> 6);
-	return (int64_t)x + (int64_t)q.nx * (y + (int64_t)q.ny * (z + (int64_t)q.nz * tt));
-}
+// Grid-stride over LEAVES of 1024 consecutive cells: the resident CTAs sweep the grid as one compact window (a few
+// t-slices), so every neighbour of the stencil has just been fetched by another CTA or is about to be its centre cell --
+// srch comes from DRAM once.  (One contiguous segment per CTA, as in the purely streaming kernels, measured 1.5x slower
+// here: the z+1 look-ahead of ~1200 independent streams does not fit into L2.)
+// SEQ (sequential-order dot products): the per-leaf sums of the products and of their magnitudes go to the segment
+// accumulators by one atomic per warp -- their order is irrelevant, they only steer the classification of pass 2.
 #ifndef FLOF_APPLY_BLK
 #define FLOF_APPLY_BLK 4
 #endif
-#ifndef FLOF_APPLY_TILED
-#define FLOF_APPLY_TILED 0
-#endif
 // STREAM: grad (read once) and tmp (written once) bypass the L2 residency competition with srch, which is read 9x
-template <bool TILED, bool STREAM = false, int MINB = FLOF_APPLY_BLK>
+template <bool STREAM, int MINB, bool SEQ>
 __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
     k_cg_apply(float4 *__restrict__ tmp, const float4 *__restrict__ srch, const float4 *__restrict__ grad,
-               int64_t cells, int64_t sY, int64_t sZ, int64_t sT, float offd, float diag, cg_tiles tiles, int multi,
+               seq_part part, int oY, int oZ, int oT, float offd, float diag, int multi, cg_seq sq,
                flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	if (st->done) return;
 	__shared__ double shd[32];
-	__shared__ double s_ar[4];
+	__shared__ double s_ar[8];
 	double dsum = 0.;
 	// cells < 2^29 (checked by the caller): 32-bit cell indices keep the eight neighbour addresses out of registers
-	const int stride = (int)(gridDim.x * blockDim.x), ncell = (int)cells;
-	const int oY = (int)sY, oZ = (int)sZ, oT = (int)sT;
-	for (int w = (int)(blockIdx.x * blockDim.x + threadIdx.x); w < ncell; w += stride) {
-		const int c = TILED ? (int)cg_tile_cell(tiles, w) : w;
-		const float4 g = STREAM ? __ldcs(grad + c) : __ldg(grad + c);
-		const float4 p = __ldg(srch + c);
-		float4 v;
-		if (is_border(g)) {
-			v = p;  // identity row
-		} else {
-			v = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (offd != 0.f) {
-				// neighbour order of nbx/nby/nbz/nbt (ref :389-392): t-1, z-1, y-1, x-1, x+1, y+1, z+1, t+1
-				const int o[8] = { -oT, -oZ, -oY, -1, 1, oY, oZ, oT };
+	for (int base = (int)blockIdx.x * SEQ_LEAF_CELLS + (int)threadIdx.x; base < part.ncells; base += (int)gridDim.x * SEQ_LEAF_CELLS) {
+		double lsum = 0.;
+		float af = 0.f;
 #pragma unroll
-				for (int m = 0; m < 8; ++m) {
-					const float4 q = __ldg(srch + (c + o[m]));
-					v.x += offd * q.x; v.y += offd * q.y; v.z += offd * q.z; v.w += offd * q.w;
+		for (int u = 0; u < SEQ_U; ++u) {
+			const int c = base + u * FLOF_BLOCK;
+			if (c < part.ncells) {
+				const float4 g = STREAM ? __ldcs(grad + c) : __ldg(grad + c);
+				const float4 p = __ldg(srch + c);
+				float4 v;
+				if (is_border(g)) {
+					v = p;  // identity row
+				} else {
+					v = make_float4(0.f, 0.f, 0.f, 0.f);
+					if (offd != 0.f) {
+						// neighbour order of nbx/nby/nbz/nbt (ref :389-392): t-1, z-1, y-1, x-1, x+1, y+1, z+1, t+1
+						const int o[8] = { -oT, -oZ, -oY, -1, 1, oY, oZ, oT };
+#pragma unroll
+						for (int m = 0; m < 8; ++m) {
+							const float4 q = __ldg(srch + (c + o[m]));
+							v.x += offd * q.x; v.y += offd * q.y; v.z += offd * q.z; v.w += offd * q.w;
+						}
+					}
+					// block row d: sum_m blockd(d,m) * x_m, blockd(d,m) = g_d*g_m (+ diag if d == m)  ref :483-488
+					const float gg[4] = { g.x, g.y, g.z, g.w };
+					const float pp[4] = { p.x, p.y, p.z, p.w };
+					float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+					for (int dd = 0; dd < 4; ++dd) {
+#pragma unroll
+						for (int m = 0; m < 4; ++m) {
+							const float b = (dd == m) ? (gg[dd] * gg[m] + diag) : (gg[dd] * gg[m]);
+							vv[dd] += b * pp[m];
+						}
+					}
+					v = make_float4(vv[0], vv[1], vv[2], vv[3]);
 				}
+				if (STREAM)
+					__stcs(tmp + c, v);
+				else
+					tmp[c] = v;
+				if (SEQ)
+					lsum += dot4a(p, v, af);
+				else
+					dsum += dot4(p, v);
 			}
-			// block row d: sum_m blockd(d,m) * x_m, blockd(d,m) = g_d*g_m (+ diag if d == m)  ref :483-488
-			const float gg[4] = { g.x, g.y, g.z, g.w };
-			const float pp[4] = { p.x, p.y, p.z, p.w };
-			float vv[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-			for (int dd = 0; dd < 4; ++dd) {
-#pragma unroll
-				for (int m = 0; m < 4; ++m) {
-					const float b = (dd == m) ? (gg[dd] * gg[m] + diag) : (gg[dd] * gg[m]);
-					vv[dd] += b * pp[m];
-				}
-			}
-			v = make_float4(vv[0], vv[1], vv[2], vv[3]);
 		}
-		if (STREAM)
-			__stcs(tmp + c, v);
-		else
-			tmp[c] = v;
-		dsum += dot4(p, v);
+		if (SEQ) {
+			// (every lane of the warp runs this: cells beyond the range contributed zero)
+			double la = (double)af;
+			for (int o = 16; o > 0; o >>= 1) {
+				lsum += __shfl_down_sync(0xffffffffu, lsum, o);
+				la += __shfl_down_sync(0xffffffffu, la, o);
+			}
+			if ((threadIdx.x & 31) == 0) {
+				const int sg = base / part.seg_cells;
+				atomicAdd(sq.aggx + sg, lsum);
+				atomicAdd(sq.agga + sg, la);
+			}
+		}
 	}
-	dsum = flof_block_sum(dsum, shd);
-	if (threadIdx.x == 0) red->dsum[0][blockIdx.x] = dsum;
+	if (!SEQ) {
+		dsum = flof_block_sum(dsum, shd);
+		if (threadIdx.x == 0) red->dsum[0][blockIdx.x] = dsum;
+	}
 	if (flof_last_block(&red->counter[1])) {
+		if (SEQ) {  // alpha1 comes from the sequential-order dot product
+			cg_seq_tail(sq, part, sq.aggx, sq.agga, 0.f, false, multi, pp, shd, s_ar);
+			for (int b = threadIdx.x; b < part.nseg; b += blockDim.x) sq.aggx[b] = sq.agga[b] = 0.;  // for the next launch
+			return;
+		}
 		double s = 0.;
 		for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += red->dsum[0][b];
 		s = flof_block_sum(s, shd);
@@ -338,20 +426,21 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 // B: alpha = sigma/alpha1; result += alpha*srch; res -= alpha*tmp; partial max(res), dot(res*precond, res)
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_cg_update(float4 *__restrict__ x, float4 *__restrict__ res, const float4 *__restrict__ srch,
-                const float4 *__restrict__ tmp, const float4 *__restrict__ grad, int64_t cells, float diag, int maxIter,
-                int multi, int defer, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
+                const float4 *__restrict__ tmp, const float4 *__restrict__ grad, seq_part part, float diag, int maxIter,
+                int multi, cg_seq sq, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	if (st->done) return;
 	__shared__ double shd[32];
 	__shared__ float shf[32];
-	__shared__ double s_ar[4];
+	__shared__ double s_ar[8];
 	const double sigma = st->sigma[st->iter & 1];
 	const double alpha = sigma / st->alpha1;  // ref :307-308
 	const double nalpha = -alpha;
 	double dsum = 0.;
+	float af = 0.f;
 	float mx = -3.402823466e+38f;
-	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
+	const int c0 = (int)blockIdx.x * part.seg_cells, c1 = min(c0 + part.seg_cells, part.ncells);
+	for (int c = c0 + (int)threadIdx.x; c < c1; c += FLOF_BLOCK) {
 		const float4 p = __ldg(srch + c), ap = __ldg(tmp + c), g = __ldg(grad + c);
 		float4 xv = x[c], r = res[c];
 		xv.x = axpy1(xv.x, alpha, p.x); xv.y = axpy1(xv.y, alpha, p.y);
@@ -362,13 +451,15 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		res[c] = r;
 		const float4 pc = precond_of(g, diag);
 		const float4 z = make_float4(r.x * pc.x, r.y * pc.y, r.z * pc.z, r.w * pc.w);
-		dsum += dot4(z, r);
+		dsum += dot4a(z, r, af);
 		mx = fmaxf(mx, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
 	}
-	dsum = flof_block_sum(dsum, shd);
+	double asum = (double)af;
+	seq_block_sum2(dsum, asum, shd);
 	mx = flof_block_max(mx, shf);
 	if (threadIdx.x == 0) {
 		red->dsum[1][blockIdx.x] = dsum;
+		red->asum[blockIdx.x] = asum;
 		red->fmax[blockIdx.x] = mx;
 	}
 	if (flof_last_block(&red->counter[2])) {
@@ -380,6 +471,15 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		}
 		s = flof_block_sum(s, shd);
 		m = flof_block_max(m, shf);
+		if (sq.on) {
+			// dot(tmp, res) comes from the sequential-order dot product, whose tail advances the state
+			m = cg_seq_tail(sq, part, red->dsum[1], red->asum, m, true, multi, pp, shd, s_ar);
+			if (threadIdx.x == 0) {
+				st->sigmaNew = s;
+				st->residual = m;
+			}
+			return;
+		}
 		if (multi == 2) {  // dot(z, res) summed and max(res) maximised over all ranks in one exchange
 			if (threadIdx.x == 0) {
 				s_ar[0] = s;
@@ -390,9 +490,8 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 			m = (float)s_ar[1];
 		}
 		if (threadIdx.x == 0) {
-			if (multi == 1 || defer) {
-				// multi == 1: raw slab results; NCCL combines them, then k_cg_update_finalize advances the state
-				// defer: dot(tmp, res) comes from the sequential-order dot product, whose tail advances the state
+			if (multi == 1) {
+				// raw slab results; NCCL combines them, then k_cg_update_finalize advances the state
 				st->sigmaNew = s;
 				st->residual = m;
 			} else {
@@ -439,57 +538,51 @@ void flof_seq_release(flof_ctx *ctx)
 {
 	flof_seq *q = ctx->seq;
 	if (!q) return;
-	cudaFree(q->desc);
-	cudaFree(q->leaf);
+	cudaFree(q->seg);
+	cudaFree(q->ent);
+	cudaFree(q->ecnt);
+	cudaFree(q->aggx);
 	cudaFree(q->pool);
 	cudaFree(q->ctl);
 	free(q);
 	ctx->seq = NULL;
 }
-static int seq_ensure(flof_ctx *ctx, int64_t nleaf)
+static int seq_ensure(flof_ctx *ctx)
 {
-	flof_seq *q = ctx->seq;
-	if (!q) {
-		q = (flof_seq *)calloc(1, sizeof(flof_seq));
-		if (!q) return flof_fail(ctx, FLOF_ERR_NOMEM, "flof_seq: out of host memory");
-		ctx->seq = q;
-		FLOF_CK(cudaMalloc((void **)&q->pool, sizeof(seq_rec) * (size_t)SEQ_POOL));
-		FLOF_CK(cudaMalloc((void **)&q->ctl, sizeof(seq_ctl)));
-		FLOF_CK(cudaMemset(q->ctl, 0, sizeof(seq_ctl)));
-		FLOF_CK(cudaFuncSetAttribute(k_seq_resolve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_RESOLVE_SMEM));
-		FLOF_CK(cudaFuncSetAttribute(k_seq_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_RESOLVE_SMEM));
-	}
-	if (nleaf > q->cap_leaves) {
-		FLOF_CK(cudaStreamSynchronize(ctx->stream));
-		if (q->desc) cudaFree(q->desc);
-		if (q->leaf) cudaFree(q->leaf);
-		q->desc = NULL;
-		q->leaf = NULL;
-		q->cap_leaves = 0;
-		FLOF_CK(cudaMalloc((void **)&q->desc, sizeof(seq_desc) * (size_t)nleaf));
-		FLOF_CK(cudaMalloc((void **)&q->leaf, sizeof(seq_rec) * (size_t)nleaf));
-		FLOF_CK(cudaMemset(q->desc, 0, sizeof(seq_desc) * (size_t)nleaf));  // stamps 0: no epoch
-		q->cap_leaves = nleaf;
-		q->epoch = 0;
-	}
+	if (ctx->seq) return FLOF_OK;
+	flof_seq *q = (flof_seq *)calloc(1, sizeof(flof_seq));
+	if (!q) return flof_fail(ctx, FLOF_ERR_NOMEM, "flof_seq: out of host memory");
+	ctx->seq = q;
+	FLOF_CK(cudaMalloc((void **)&q->seg, sizeof(seq_seg) * FLOF_MAX_PARTIALS));
+	FLOF_CK(cudaMalloc((void **)&q->ent, sizeof(seq_rec) * (size_t)FLOF_MAX_PARTIALS * SEQ_ECAP));
+	FLOF_CK(cudaMalloc((void **)&q->ecnt, sizeof(int) * FLOF_MAX_PARTIALS));
+	FLOF_CK(cudaMalloc((void **)&q->aggx, sizeof(double) * 2 * FLOF_MAX_PARTIALS));
+	FLOF_CK(cudaMemset(q->aggx, 0, sizeof(double) * 2 * FLOF_MAX_PARTIALS));
+	q->agga = q->aggx + FLOF_MAX_PARTIALS;
+	FLOF_CK(cudaMalloc((void **)&q->pool, sizeof(seq_rec) * (size_t)SEQ_POOL));
+	FLOF_CK(cudaMalloc((void **)&q->ctl, sizeof(seq_ctl)));
+	FLOF_CK(cudaMemset(q->ctl, 0, sizeof(seq_ctl)));
+	FLOF_CK(cudaFuncSetAttribute(k_seq_resolve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_RESOLVE_SMEM));
+	FLOF_CK(cudaFuncSetAttribute(k_seq_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_RESOLVE_SMEM));
 	return FLOF_OK;
 }
-// enqueues one dot product over `ncells` cells starting at a / b; total_products = 4 * cells of ALL ranks (error margin)
-static int seq_dot(flof_ctx *ctx, int kind, const float4 *a, const float4 *b, int64_t ncells, float diag, int mode,
-                   float accuracy, int maxIter, flof_cg_state *st, int64_t total_products, int multi, const double *off)
+static seq_args seq_make_args(flof_ctx *ctx, seq_part part, int64_t total_products)
 {
-	const int64_t nleaf = (ncells + SEQ_LEAF_CELLS - 1) / SEQ_LEAF_CELLS;
-	FLOF_ARG(ncells > 0 && ncells < ((int64_t)1 << 31), "flof_seq: cell count out of range");
-	FLOF_RET(seq_ensure(ctx, nleaf));
 	flof_seq *q = ctx->seq;
 	seq_args A;
-	A.desc = q->desc; A.leaf = q->leaf; A.pool = q->pool; A.ctl = q->ctl; A.off = off;
-	A.epoch = ++q->epoch;
-	A.nleaf = (int)nleaf;
-	A.ncells = (int)ncells;
+	A.seg = q->seg; A.ent = q->ent; A.ecnt = q->ecnt; A.pool = q->pool; A.ctl = q->ctl;
+	A.part = part;
 	A.kf = seq_margin_factor(total_products);
-	int64_t cap = (int64_t)ctx->sm_count * 6;
-	const int blocks = (int)(nleaf < cap ? nleaf : cap);
+	return A;
+}
+// pass 2 + resolve of one dot product whose pass 1 (per-segment prefixes in A.seg) has been enqueued
+static int seq_dot(flof_ctx *ctx, int kind, const float4 *a, const float4 *b, float diag, const seq_args &A, int mode,
+                   float accuracy, int maxIter, flof_cg_state *st, int multi)
+{
+	// every CTA folds the same number of segments (+-1): one per CTA up to 4 CTAs per SM, else two, ...
+	const int cap = ctx->sm_count * 4;
+	const int per = (A.part.nseg + cap - 1) / cap;
+	const int blocks = (A.part.nseg + per - 1) / per;
 	const flof_p2p_dev pp = ctx->p2p.dev;
 	if (kind == 0) {
 		FLOF_LAUNCH(k_dot_seq<0>, blocks, FLOF_BLOCK, 0, a, b, diag, A, st);
@@ -501,16 +594,10 @@ static int seq_dot(flof_ctx *ctx, int kind, const float4 *a, const float4 *b, in
 	return FLOF_OK;
 }
 
-// test / tool entry: the sequential-order sum of a[i]*b[i] (kind 0) or (a[i]*precond(b)[i])*a[i] (kind 1) over
-// `cells` Vec4 cells.  stats (optional, 6 values): dots, dirty leaves, raw products, pieces, fallbacks, inconsistencies
-// since the context was created.
-extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag,
-                            double *result, unsigned long long *stats)
+static int seq_read_stats(flof_ctx *ctx, double *result, unsigned long long *stats, const char *who)
 {
-	FLOF_ARG(kind == 0 || kind == 1, "flof_dot_seq: kind must be 0 or 1");
-	FLOF_RET(seq_dot(ctx, kind, (const float4 *)a, (const float4 *)b, cells, diag, SEQ_MODE_NONE, 0.f, 0, NULL, 4 * cells, 0, NULL));
 	seq_ctl *h = (seq_ctl *)malloc(sizeof(seq_ctl));
-	if (!h) return flof_fail(ctx, FLOF_ERR_NOMEM, "flof_dot_seq: out of host memory");
+	if (!h) return flof_fail(ctx, FLOF_ERR_NOMEM, "%s: out of host memory", who);
 	cudaError_t e = cudaMemcpyAsync(h, ctx->seq->ctl, sizeof(seq_ctl), cudaMemcpyDeviceToHost, ctx->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 	if (e == cudaSuccess) {
@@ -518,28 +605,37 @@ extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64
 		if (stats) {
 			stats[0] = h->n_dots; stats[1] = h->n_dirty; stats[2] = h->n_raw;
 			stats[3] = h->n_pieces; stats[4] = h->n_fallback; stats[5] = h->n_inconsistent;
+			stats[6] = h->n_slow_segments;
+			stats[7] = h->n_inexact;
 		}
 	}
 	free(h);
-	if (e != cudaSuccess) return flof_fail(ctx, FLOF_ERR_CUDA, "flof_dot_seq: %s", cudaGetErrorString(e));
+	if (e != cudaSuccess) return flof_fail(ctx, FLOF_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
 	return FLOF_OK;
+}
+// test / tool entry: the sequential-order sum of a[i]*b[i] (kind 0) or (a[i]*precond(b)[i])*a[i] (kind 1) over
+// `cells` Vec4 cells.  stats (optional, 8 values): dots, dirty leaves, raw products, pieces, fallbacks, inconsistencies,
+// careful segments, inexact (tree-sum) fallbacks since the context was created.
+extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag,
+                            double *result, unsigned long long *stats)
+{
+	FLOF_ARG(kind == 0 || kind == 1, "flof_dot_seq: kind must be 0 or 1");
+	FLOF_ARG(cells > 0 && cells < ((int64_t)1 << 29), "flof_dot_seq: cell count out of range");
+	FLOF_RET(seq_ensure(ctx));
+	const seq_args A = seq_make_args(ctx, seq_make_part(cells, 0, ctx->sm_count), 4 * cells);
+	if (kind == 0)
+		FLOF_LAUNCH(k_seq_agg<0>, A.part.nseg, FLOF_BLOCK, 0, (const float4 *)a, (const float4 *)b, diag, A, ctx->red);
+	else
+		FLOF_LAUNCH(k_seq_agg<1>, A.part.nseg, FLOF_BLOCK, 0, (const float4 *)a, (const float4 *)b, diag, A, ctx->red);
+	FLOF_RET(seq_dot(ctx, kind, (const float4 *)a, (const float4 *)b, diag, A, SEQ_MODE_NONE, 0.f, 0, NULL, 0));
+	return seq_read_stats(ctx, result, stats, "flof_dot_seq");
 }
 extern "C" int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats)
 {
 	FLOF_ARG(stats != NULL, "flof_seq_stats: stats is NULL");
-	for (int i = 0; i < 6; ++i) stats[i] = 0;
+	for (int i = 0; i < 8; ++i) stats[i] = 0;
 	if (!ctx->seq) return FLOF_OK;
-	seq_ctl *h = (seq_ctl *)malloc(sizeof(seq_ctl));
-	if (!h) return flof_fail(ctx, FLOF_ERR_NOMEM, "flof_seq_stats: out of host memory");
-	cudaError_t e = cudaMemcpyAsync(h, ctx->seq->ctl, sizeof(seq_ctl), cudaMemcpyDeviceToHost, ctx->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-	if (e == cudaSuccess) {
-		stats[0] = h->n_dots; stats[1] = h->n_dirty; stats[2] = h->n_raw;
-		stats[3] = h->n_pieces; stats[4] = h->n_fallback; stats[5] = h->n_inconsistent;
-	}
-	free(h);
-	if (e != cudaSuccess) return flof_fail(ctx, FLOF_ERR_CUDA, "flof_seq_stats: %s", cudaGetErrorString(e));
-	return FLOF_OK;
+	return seq_read_stats(ctx, NULL, stats, "flof_seq_stats");
 }
 
 static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, const float *grad,
@@ -560,28 +656,43 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 	}
 	const flof_p2p_dev pp = ctx->p2p.dev;
 	const int64_t n = c1 - c0;
-	const int blocks = flof_flat_blocks(ctx, n, 8);
+	FLOF_ARG(n < ((int64_t)1 << 29), "opticalFlow4d: too many cells per rank");
+	// one CTA per contiguous segment of the range (reducing kernels); the direction kernel stays a flat grid-stride loop
+	const int apply_variant = ctx->opt.apply_variant;
+	const seq_part part = seq_make_part(n, sT, ctx->sm_count);
+	const int blocks = part.nseg;
+	// the stencil kernel sweeps the grid leaf by leaf (grid-stride), at the occupancy of its variant
+	const int64_t nleaf = (n + SEQ_LEAF_CELLS - 1) / SEQ_LEAF_CELLS;
+	const int aper = apply_variant == 0 || apply_variant == 1 ? 4 : (apply_variant == 5 ? 6 : 8);
+	const int ablocks = (int)(nleaf < (int64_t)ctx->sm_count * aper ? nleaf : (int64_t)ctx->sm_count * aper);
+	const int dblocks = flof_flat_blocks(ctx, n, 8);
 	float4 *X = (float4 *)x + c0, *R = (float4 *)res + c0, *P = (float4 *)srch + c0, *AP = (float4 *)tmp + c0;
 	const float4 *G = (const float4 *)grad + c0, *B = (const float4 *)rhs + c0;
 	const size_t slice_bytes = sizeof(float4) * (size_t)sT;
-	// (the brick traversal measured slower than the flat one on B200: 0.26 vs 0.21 ms at 64^4 -- kept behind a
-	// compile-time switch; the flat kernel is DRAM-latency bound, not L2-bandwidth bound)
-	const bool tiled = FLOF_APPLY_TILED && (d.nx % 8 == 0) && (d.ny % 8 == 0) && (d.nz % 4 == 0);
-	const cg_tiles tiles = { d.nx / 8, d.ny / 8, d.nz / 4, d.nx, d.ny, d.nz };  // brick traversal of the apply kernel (slab-local t)
-	// dot products in the reference's sequential order (default, single GPU): the reducing kernels keep their max /
-	// tree sums but leave the state alone (defer); k_dot_seq + k_seq_resolve deliver the exact sums and advance it
-	const int seq = (ctx->opt.dot_mode == 1 && !multi) ? 1 : 0;
-	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, X, R, P, G, B, n, k.diag, accuracy, multi, seq, pp, ctx->red, ctx->cg);
-	if (seq) FLOF_RET(seq_dot(ctx, 1, R, G, n, k.diag, SEQ_MODE_INIT, accuracy, maxIter, ctx->cg, 4 * cells, 0, NULL));
+	// dot products in the reference's sequential order (default): the reducing kernels leave per-segment prefixes
+	// (pass 1), k_dot_seq + k_seq_resolve deliver the exact sums and advance the state.  On a sharded level this needs
+	// the peer mailboxes (the exact running sum travels from rank to rank); the NCCL fallback keeps tree sums.
+	const int seq = (ctx->opt.dot_mode == 1 && multi != 1) ? 1 : 0;
+	cg_seq sq = { 0, NULL, NULL, NULL, NULL };
+	seq_args SA;
+	memset(&SA, 0, sizeof(SA));
+	if (seq) {
+		FLOF_RET(seq_ensure(ctx));
+		SA = seq_make_args(ctx, part, 4 * cells);
+		sq.on = 1;
+		sq.seg = ctx->seq->seg;
+		sq.ctl = ctx->seq->ctl;
+		sq.aggx = ctx->seq->aggx;
+		sq.agga = ctx->seq->agga;
+	}
+	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, X, R, P, G, B, part, k.diag, accuracy, multi, sq, pp, ctx->red, ctx->cg);
+	if (seq) FLOF_RET(seq_dot(ctx, 1, R, G, k.diag, SA, SEQ_MODE_INIT, accuracy, maxIter, ctx->cg, multi));
 	if (multi == 1) {
 		FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
 		FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));
 		FLOF_LAUNCH(k_cg_init_finalize, 1, 1, 0, accuracy, ctx->cg);
 	}
 	flof_cg_state *h = (flof_cg_state *)ctx->pinned;
-	// measured at 64^4 (tools/bench_kernel.py): 7 = streaming hints + 32 registers / 8 CTAs per SM 0.156 ms, against
-	// 0.21-0.22 ms for the 4..6-CTA variants: the kernel is DRAM-latency bound and full occupancy hides it
-	const int apply_variant = ctx->opt.apply_variant;
 	int launched = 0;
 	// poll the device-side done flag every `chunk` iterations; iterations after convergence are
 	// no-op kernels (early return on st->done)
@@ -592,35 +703,32 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 		if (h->done || launched >= maxIter) break;
 		for (int q = 0; q < chunk && launched < maxIter; ++q, ++launched) {
 			if (multi) FLOF_RET(flof_halo_exchange(ctx, srch, d.nt, slice_bytes, 1));
-			if (tiled)
-				FLOF_LAUNCH(k_cg_apply<true>, blocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, n, sY, sZ, sT, k.offd, k.diag, tiles,
-				            multi, pp, ctx->red, ctx->cg);
-			else {
-#define FLOF_APPLY_LAUNCH(...)                                                                                           \
-	FLOF_LAUNCH((k_cg_apply<__VA_ARGS__>), blocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, n, sY, sZ, sT, k.offd, k.diag, \
-	            tiles, multi, pp, ctx->red, ctx->cg)
-				switch (apply_variant) {
-				case 1: FLOF_APPLY_LAUNCH(false, true, 4); break;
-				case 2: FLOF_APPLY_LAUNCH(false, false, 5); break;
-				case 3: FLOF_APPLY_LAUNCH(false, true, 5); break;
-				case 4: FLOF_APPLY_LAUNCH(false, false, 6); break;
-				case 5: FLOF_APPLY_LAUNCH(false, true, 6); break;
-				case 6: FLOF_APPLY_LAUNCH(false, false, 3); break;
-				case 7: FLOF_APPLY_LAUNCH(false, true, 8); break;
-				default: FLOF_APPLY_LAUNCH(false, false, 4); break;
-				}
+#define FLOF_APPLY_LAUNCH(STREAM, MINB)                                                                                       \
+	do {                                                                                                                      \
+		if (seq)                                                                                                              \
+			FLOF_LAUNCH((k_cg_apply<STREAM, MINB, true>), ablocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, part, (int)sY,    \
+			            (int)sZ, (int)sT, k.offd, k.diag, multi, sq, pp, ctx->red, ctx->cg);                                 \
+		else                                                                                                                  \
+			FLOF_LAUNCH((k_cg_apply<STREAM, MINB, false>), ablocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, part, (int)sY,   \
+			            (int)sZ, (int)sT, k.offd, k.diag, multi, sq, pp, ctx->red, ctx->cg);                                 \
+	} while (0)
+			switch (apply_variant) {
+			case 0: FLOF_APPLY_LAUNCH(false, 4); break;
+			case 1: FLOF_APPLY_LAUNCH(true, 4); break;
+			case 5: FLOF_APPLY_LAUNCH(true, 6); break;
+			default: FLOF_APPLY_LAUNCH(true, 8); break;  // 7
 			}
 			if (multi == 1) FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->alpha1, 1));
-			if (seq) FLOF_RET(seq_dot(ctx, 0, P, AP, n, k.diag, SEQ_MODE_ALPHA, accuracy, maxIter, ctx->cg, 4 * cells, 0, NULL));
-			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, X, R, (const float4 *)P, (const float4 *)AP, G, n, k.diag, maxIter, multi,
-			            seq, pp, ctx->red, ctx->cg);
-			if (seq) FLOF_RET(seq_dot(ctx, 1, R, G, n, k.diag, SEQ_MODE_ADVANCE, accuracy, maxIter, ctx->cg, 4 * cells, 0, NULL));
+			if (seq) FLOF_RET(seq_dot(ctx, 0, P, AP, k.diag, SA, SEQ_MODE_ALPHA, accuracy, maxIter, ctx->cg, multi));
+			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, X, R, (const float4 *)P, (const float4 *)AP, G, part, k.diag, maxIter, multi,
+			            sq, pp, ctx->red, ctx->cg);
+			if (seq) FLOF_RET(seq_dot(ctx, 1, R, G, k.diag, SA, SEQ_MODE_ADVANCE, accuracy, maxIter, ctx->cg, multi));
 			if (multi == 1) {
 				FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
 				FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));
 				FLOF_LAUNCH(k_cg_update_finalize, 1, 1, 0, maxIter, ctx->cg);
 			}
-			FLOF_LAUNCH(k_cg_direction, blocks, FLOF_BLOCK, 0, P, (const float4 *)R, G, n, k.diag, ctx->cg);
+			FLOF_LAUNCH(k_cg_direction, dblocks, FLOF_BLOCK, 0, P, (const float4 *)R, G, n, k.diag, ctx->cg);
 		}
 		if (launched >= 32) chunk = 16;
 	}

@@ -14,6 +14,7 @@
 // a 4-sequence (:182-193); every call accepts notiming= (added by the Python shim at the bottom);
 // errors surface as RuntimeError (pwrapper/pclass.cpp:50-54).  There is no CPU fallback: the module
 // fails to create a Solver without a CUDA device.
+#include <unistd.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/eval.h>
 #include <pybind11/stl.h>
@@ -789,7 +790,11 @@ PYBIND11_MODULE(manta, m)
 		try {
 			IoPool::get().drain();
 		} catch (const std::exception &e) {
+			// nobody called flushUniWrites(): a lost .uni write must not look like success to the calling process
 			fprintf(stderr, "flof-b200: background .uni write failed: %s\n", e.what());
+			fflush(stderr);
+			IoPool::get().shutdown();
+			_exit(74);  // EX_IOERR
 		}
 		IoPool::get().shutdown();
 	}));

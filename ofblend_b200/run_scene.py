@@ -46,7 +46,13 @@ def main(argv):
     import manta  # noqa: F401  (fails loudly if the module is not built or there is no GPU)
     sys.argv = [scene] + list(argv[2:])
     _load_helpers_py3(scene_dir)
-    runpy.run_path(scene, run_name="__main__")
+    try:
+        runpy.run_path(scene, run_name="__main__")
+    finally:
+        # Grid.save() returns before the background deflate + write has finished (overlapped .uni I/O): wait for it
+        # here so that a failed write (disk full, I/O error) raises and the process exits non-zero, like the
+        # reference's synchronous save() would have (ref fileio.cpp:834-902)
+        manta.flushUniWrites()
     return 0
 
 

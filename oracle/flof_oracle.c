@@ -377,81 +377,8 @@ static void apply_mat(const orc_mat *m, const float *x, float *y, i64 N)
  * summed in 4096-element blocks first.  Used to measure how much the reference's own result moves
  * when only the order of the fp64 dot-product summation changes (DESIGN.md "conditioning"). */
 static int g_dot_mode = 0;
-static int g_gpu_sms = 148; /* B200 */
 void orc_set_dot_mode(int m) { g_dot_mode = m; }
-void orc_set_gpu_sm_count(int n) { g_gpu_sms = n; }
 
-/* mode 2: the summation ORDER of the CUDA kernels (ofblend_b200/csrc/flof_solve.cu k_cg_*):
- * 256-thread blocks, grid = min(ceil(cells/256), 8*SMs, 2048), grid-stride loop over cells, per
- * cell the 4 component products are summed first (dot4), per-thread fp64 accumulation, warp
- * shuffle-down tree, 8 warp sums reduced by warp 0, per-block partials summed by one block in a
- * strided loop + the same block tree.  Same fp32 products, same fp64 adds -- only the order differs
- * from the reference.  With this mode the oracle reproduces the GPU bit-for-bit, which isolates
- * the summation order as the ONLY difference between the GPU path and the reference. */
-static double warp_tree(double *v) /* emulates flof_warp_sum over 32 lanes, result of lane 0 */
-{
-	for (int o = 16; o > 0; o >>= 1) {
-		double n[32];
-		for (int l = 0; l < 32; ++l) n[l] = v[l] + (l + o < 32 ? v[l + o] : v[l]);
-		for (int l = 0; l < 32; ++l) v[l] = n[l];
-	}
-	return v[0];
-}
-static double block_tree(const double *t) /* flof_block_sum for blockDim 256 */
-{
-	double sh[32];
-	for (int w = 0; w < 8; ++w) {
-		double v[32];
-		for (int l = 0; l < 32; ++l) v[l] = t[w * 32 + l];
-		sh[w] = warp_tree(v);
-	}
-	double v[32];
-	for (int l = 0; l < 32; ++l) v[l] = l < 8 ? sh[l] : 0.0;
-	return warp_tree(v);
-}
-/* cell visited by work index w of k_cg_apply<TILED> (8 x 8 x 4 bricks), see flof_solve.cu cg_tile_cell */
-static int g_dot_tiled = 0;
-static orc_dim4 g_dot_dims;
-static i64 gpu_tile_cell(orc_dim4 d, i64 w)
-{
-	const unsigned ntx = d.nx / 8, nty = d.ny / 8, ntz = d.nz / 4;
-	const unsigned T = (unsigned)(w >> 8), tid = (unsigned)w & 255u;
-	const unsigned tx = T % ntx, r1 = T / ntx, ty = r1 % nty, r2 = r1 / nty, tz = r2 % ntz, tt = r2 / ntz;
-	const unsigned x = tx * 8 + (tid & 7), y = ty * 8 + ((tid >> 3) & 7), z = tz * 4 + (tid >> 6);
-	return (i64)x + (i64)d.nx * (y + (i64)d.ny * (z + (i64)d.nz * tt));
-}
-static double dot_prod_gpu_order(const float *a, const float *b, i64 N)
-{
-	const i64 cells = N / 4;
-	i64 need = (cells + 255) / 256, cap = (i64)g_gpu_sms * 8;
-	if (cap > 2048) cap = 2048;
-	if (need < 1) need = 1;
-	const int blocks = (int)(need < cap ? need : cap);
-	const i64 T = (i64)blocks * 256;
-	double *acc = (double *)calloc((size_t)T, sizeof(double));
-	const int tiled = g_dot_tiled && g_dot_dims.nx % 8 == 0 && g_dot_dims.ny % 8 == 0 && g_dot_dims.nz % 4 == 0;
-	for (i64 w = 0; w < cells; ++w) {
-		const i64 c = tiled ? gpu_tile_cell(g_dot_dims, w) : w;
-		const float *x = a + c * 4, *y = b + c * 4;
-		double s = (double)(x[0] * y[0]);
-		s += (double)(x[1] * y[1]);
-		s += (double)(x[2] * y[2]);
-		s += (double)(x[3] * y[3]);
-		acc[w % T] += s;
-	}
-	double *part = (double *)calloc((size_t)blocks, sizeof(double));
-	for (int bl = 0; bl < blocks; ++bl) part[bl] = block_tree(acc + (i64)bl * 256);
-	double t[256];
-	for (int th = 0; th < 256; ++th) {
-		double s = 0.;
-		for (int bl = th; bl < blocks; bl += 256) s += part[bl];
-		t[th] = s;
-	}
-	const double r = block_tree(t);
-	free(acc);
-	free(part);
-	return r;
-}
 /* test probes for the CUDA path's sequential-order dot products (flof_dot_seq): the reference's loops, nothing else.
  * kind 0: dotProd(a, b) (:234-241).  kind 1: precondInit + precondApply + dotProd(tmp, res) (:331-354, :296, :319) with
  * a = res and the Jacobi diagonal of the matrix-free form: grad_d^2 + diag, 1 on identity rows (grad.x = NaN marker). */
@@ -475,7 +402,6 @@ double orc_dot_seq(const float *a, const float *b, long long cells, int kind, fl
 }
 static double dot_prod(const float *a, const float *b, i64 N)
 {
-	if (g_dot_mode == 2) return dot_prod_gpu_order(a, b, N);
 	if (g_dot_mode == 1) {
 		double tot = 0.;
 		for (i64 s = 0; s < N; s += 4096) {

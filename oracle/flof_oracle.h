@@ -24,10 +24,9 @@ extern "C" {
 typedef struct { int nx, ny, nz, nt; } orc_dim4;
 
 int orc_set_threads(int n);
-/* CG dot-product summation order: 0 sequential (the reference), 1 blocked (conditioning probe),
- * 2 the CUDA kernels' reduction order for a GPU with orc_set_gpu_sm_count() SMs (default 148) */
+/* CG dot-product summation order: 0 sequential (the reference), 1 blocked (conditioning probe: how far the
+ * reference's own result moves when only the order of the fp64 sums changes) */
 void orc_set_dot_mode(int m);
-void orc_set_gpu_sm_count(int n);
 /* the reference's sequential dot-product loops on their own (checker of flof_dot_seq) */
 double orc_dot_seq(const float *a, const float *b, long long cells, int kind, float diag);
 

@@ -215,24 +215,23 @@ def test_multiscale_small(gpu):
     assert np.abs(adv_a - adv_b).max() / 0.005 <= SDF_TOL
 
 
-def test_mode1_bit_exact_in_gpu_summation_order(gpu):
-    """The ONLY arithmetic difference between the CUDA path and the reference is the order in which
-    the CG's fp64 dot products are summed.  Proof: the oracle with its dot products switched to the
-    kernels' reduction order (oracle/flof_oracle.c dot mode 2; mode 0 is bit-identical to the
-    reference) reproduces the GPU deformation of a full README-parameter mode-1 solve bit for bit."""
+def test_tree_dot_mode_stays_inside_the_references_own_band(gpu):
+    """dot_mode 0 (tree reductions, the faster non-default option): same CG stopping iterations, pre-projection field
+    within the 1e-4 bar; the default (dot_mode 1, reference summation order) is held to identical bits in
+    tests/test_gpu_seqsum.py."""
     from ofblend_b200 import synth
     dims = (32, 32, 32, 24)
     i0 = synth.post_process(synth.two_drop_phi(dims, 0), port)
     i1 = synth.post_process(synth.two_drop_phi(dims, 1), port)
     v0 = np.zeros(i0.shape + (4,), np.float32)
-    a, it_a, err_a = gpu.optical_flow_multiscale4d(v0, i0, i1, want_trace=True, **synth.MODE1_PARAMS)
-    lib = port.lib()
-    lib.orc_set_gpu_sm_count(gpu.ctx.sm_count)
-    lib.orc_set_dot_mode(2)
+    kw = dict(synth.MODE1_PARAMS)
+    kw["doFinalProject"] = False
+    gpu.ctx.set_option("dot_mode", 0)
     try:
-        b, it_b, err_b = port.optical_flow_multiscale4d(v0, i0, i1, want_trace=True, **synth.MODE1_PARAMS)
+        a, it_a, err_a = gpu.optical_flow_multiscale4d(v0, i0, i1, want_trace=True, **kw)
     finally:
-        lib.orc_set_dot_mode(0)
+        gpu.ctx.set_option("dot_mode", 1)
+    b, it_b, err_b = port.optical_flow_multiscale4d(v0, i0, i1, want_trace=True, **kw)
     assert it_a == it_b
-    eq(a, b)
-    assert np.allclose(err_a, err_b, rtol=1e-6)
+    assert rel_l2(a, b) <= DEFO_TOL
+    assert np.allclose(err_a, err_b, rtol=1e-5)

@@ -58,7 +58,7 @@ def main():
         ctx._chk(ctx.lib.flof_profile_end(ctx.h, stats, 64, C.byref(n)))
         for q in range(n.value):
             s = stats[q]
-            if s.total_ms / s.launches > 0.02:
+            if s.total_ms / s.launches > 0.004:
                 print("%-8s %-44s launches %4d  avg %8.4f ms   %7.1f ns/Mcell" % (
                     name, s.name.decode()[:44], s.launches, s.total_ms / s.launches, s.total_ms / s.launches * 1e6 / (cells / 1e6) / 1e3))
     ctx.close()
