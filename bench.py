@@ -43,8 +43,9 @@ UNIT = "s"
 # algorithmic bytes per cell and launch (SURVEY.md §8d / DESIGN.md §4)
 KERNEL_BYTES_PER_CELL = {
     "k_cg_apply": 48,         # srch 16 + grad 16 -> tmp 16
-    "k_cg_update": 112,       # result, res, srch, tmp, grad 80 -> result, res 32
-    "k_cg_direction": 64,     # res, grad, srch 48 -> srch 16
+    "k_cg_update": 128,       # result, res, srch, tmp, grad 80 -> result, res, res*precond 48
+    "k_cg_direction": 48,     # res*precond, srch 32 -> srch 16
+    "k_dot_seq": 32,          # the two vectors of a sequential-order dot product, read once
     "k_gauss_blur4d": 32,     # Vec4 in 16 -> Vec4 out 16 per pass
     "k_cv_expol_blur4d": 36,  # a 16 + marker 4 -> tmp 16 (dense kernel: every cell read and written)
     "k_cv_expol_planes": 36,  # component-plane work-list kernel (default): same algorithmic sweep

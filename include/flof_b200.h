@@ -86,7 +86,7 @@ int flof_ctx_comm_destroy(flof_ctx *ctx);
 int flof_ctx_rank(flof_ctx *ctx);
 int flof_ctx_nranks(flof_ctx *ctx);
 /* kernel selection knobs, all bit-identical (A/B timing, tests): "expol_mode" 1 Vec4 work list (default) / 0 component
- * planes / 2 dense; "expol_variant", "apply_variant" register-budget variants (apply: 7 = default).  Defaults come from the environment
+ * planes / 2 dense; "expol_variant", "apply_variant" register-budget variants (apply: 11 = default).  Defaults come from the environment
  * variables FLOF_EXPOL_MODE, FLOF_EXPOL_VARIANT, FLOF_APPLY_VARIANT when the context is created. */
 int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value);
 /* "dot_mode": 1 (default, FLOF_DOT_MODE) = the CG's dot products are evaluated in the reference's SEQUENTIAL summation
@@ -94,8 +94,8 @@ int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value);
  * which makes the whole mode-1 result bit-identical to the reference; 0 = tree reductions (last bits of the sums differ).
  * flof_dot_seq is that dot product on its own (tests, tools): kind 0 = sum a[i]*b[i], kind 1 = sum (a[i]*precond(b)[i])*a[i]
  * with the Jacobi reciprocal diagonal of grad = b (ref: precondInit/precondApply :331-354); `cells` Vec4 cells.
- * stats[8] = dot products, dirty leaves, raw products, pieces, fallbacks, failed consistency checks, segments that took
- * the careful (leaf-by-leaf) path, fallbacks that had to return the tree sum -- all since the context was created. */
+ * stats[9] = dot products, dirty leaves, raw products, pieces, fallbacks, failed consistency checks, segments that took
+ * the careful (leaf-by-leaf) path, fallbacks that had to return the tree sum, OR of the reason flags of the fallbacks -- all since the context was created. */
 int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag, double *result,
                  unsigned long long *stats);
 int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats);

@@ -75,8 +75,9 @@ int flof_ctx_create(flof_ctx **out, int device)
 	c->shard_min_cells = (int64_t)1 << 22;
 	c->opt.expol_mode = getenv("FLOF_EXPOL_MODE") ? atoi(getenv("FLOF_EXPOL_MODE")) : 1;
 	c->opt.expol_variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
-	c->opt.apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 7;
+	c->opt.apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 11;
 	c->opt.dot_mode = getenv("FLOF_DOT_MODE") ? atoi(getenv("FLOF_DOT_MODE")) : 1;
+	c->opt.no_p2p = getenv("FLOF_NO_P2P") ? 1 : 0;
 	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CCK(cudaDeviceGetDefaultMemPool(&c->pool, device));
 	uint64_t thr = UINT64_MAX;
@@ -120,6 +121,7 @@ int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value)
 	else if (!strcmp(name, "expol_variant")) ctx->opt.expol_variant = value;
 	else if (!strcmp(name, "apply_variant")) ctx->opt.apply_variant = value;
 	else if (!strcmp(name, "dot_mode")) ctx->opt.dot_mode = value;
+	else if (!strcmp(name, "no_p2p")) ctx->opt.no_p2p = value;
 	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_set_option: unknown option '%s'", name);
 	return FLOF_OK;
 }

@@ -170,12 +170,13 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 	// selectable for further work.  2: dense kernel (no work list).
 	const int mode = ctx->opt.expol_mode;
 	const int64_t cap4 = mode == 0 ? flof_expol_planes_capacity(ctx, d) : 0;
-	const int64_t cap1 = (mode <= 1 && cap4 == 0) ? flof_expol_item_capacity(ctx, d) : 0;
+	const int64_t capz = mode == 3 ? flof_expol_z2_capacity(ctx, d) : 0;  // 3: Vec4 work list with 4y x 2z items
+	const int64_t cap1 = ((mode <= 1 || mode == 3) && cap4 == 0 && capz == 0) ? flof_expol_item_capacity(ctx, d) : 0;
 	void *tmp = NULL, *tmp2 = NULL, *items = NULL, *count = NULL;
 	int rc = flof_tmp_alloc(ctx, &tmp, bytes, false);
 	int n = 0;
-	if (rc == FLOF_OK && (cap4 > 0 || cap1 > 0)) {
-		rc = flof_tmp_alloc(ctx, &items, (cap4 > 0 ? sizeof(uint2) * (size_t)cap4 : sizeof(uint32_t) * (size_t)cap1), false);
+	if (rc == FLOF_OK && (cap4 > 0 || cap1 > 0 || capz > 0)) {
+		rc = flof_tmp_alloc(ctx, &items, (cap4 > 0 ? sizeof(uint2) * (size_t)cap4 : (capz > 0 ? sizeof(uint2) * (size_t)capz : sizeof(uint32_t) * (size_t)cap1)), false);
 		if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &count, sizeof(unsigned int), false);
 	}
 	if (rc == FLOF_OK && cap4 > 0) {
@@ -193,15 +194,20 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 		if (rc == FLOF_OK) rc = flof_expol_from_planes(ctx, a, cur, d);
 	} else if (rc == FLOF_OK) {
 		float *cur = a, *oth = (float *)tmp;
-		if (cap1 > 0) {
+		if (cap1 > 0 || capz > 0) {
 			// Vec4 work list: the cells that never change are copied into the second buffer once
-			rc = flof_expol_build(ctx, marker, d, (uint32_t *)items, (unsigned int *)count, &n);
+			if (capz > 0)
+				rc = flof_expol_z2_build(ctx, marker, d, (uint2 *)items, (unsigned int *)count, &n);
+			else
+				rc = flof_expol_build(ctx, marker, d, (uint32_t *)items, (unsigned int *)count, &n);
 			if (rc == FLOF_OK) rc = flof_memcpy_d2d(ctx, oth, cur, bytes);
 		}
 		for (int sIt = 0; sIt < sweeps && rc == FLOF_OK; ++sIt) {
 			rc = flof_halo_exchange(ctx, cur, d.nt, slice_bytes, 1);
 			if (rc != FLOF_OK) break;
-			if (cap1 > 0)
+			if (capz > 0)
+				rc = flof_launch_expol_z2(ctx, cur, oth, (const uint2 *)items, n, d);
+			else if (cap1 > 0)
 				rc = flof_launch_expol_items(ctx, cur, oth, (const uint32_t *)items, n, d);
 			else
 				rc = flof_launch_expol_tiled(ctx, cur, oth, marker, d);

@@ -362,6 +362,160 @@ static int flof_launch_expol_items(flof_ctx *ctx, const float *a, float *out, co
 	return FLOF_OK;
 }
 
+// ------------------------------------------------------------------ 81-tap extrapolation, work list, 4y x 2z items ---
+// Same work-list scheme with items of FLOF_ETPY rows x 2 z-planes: the 18 row segments of a (vt, plane) pair feed the
+// outputs of both z-planes, so an output costs 27 LDG.128 instead of 40.5 (the kernel is bound by the L1 data pipe,
+// not by its 648 packed adds per item).  Per output the taps still arrive in the reference's order (vt, zk, yj, xi):
+// planes ascend, rows ascend within a plane, and every accumulator only ever sees the planes of its own window.
+// item = { linear id ((tl*nzb + kb)*nyb + yb)*nx + x , need-mask: bit (zo*FLOF_ETPY + oy) }
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_expol_build_items_z2(const float *__restrict__ mark, uint2 *__restrict__ items, unsigned int *__restrict__ count,
+                           flof_kd d, int nyb)
+{
+	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
+	const int kb = (int)blockIdx.y, tl = (int)blockIdx.z, t = tl + d.t0;
+	const int nzb = (d.nz + 1) / 2;
+	unsigned mask = 0;
+	uint32_t id = 0;
+	if (p < (unsigned)(d.nx * nyb) && t >= 1 && t < d.nt - 1) {
+		const int yb = (int)(p / (unsigned)d.nx), x = (int)(p - (unsigned)yb * (unsigned)d.nx);
+		if (x >= 1 && x < d.nx - 1) {
+#pragma unroll
+			for (int zo = 0; zo < 2; ++zo) {
+				const int k = kb * 2 + zo;
+				if (k < 1 || k >= d.nz - 1) continue;
+				const int64_t plane = flof_idx(d, x, 0, k, t);
+#pragma unroll
+				for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+					const int y = yb * FLOF_ETPY + oy;
+					if (y >= 1 && y < d.ny - 1 && __ldg(mark + plane + (int64_t)y * d.nx) == 0.f) mask |= 1u << (zo * FLOF_ETPY + oy);
+				}
+			}
+		}
+		id = (uint32_t)(((tl * nzb + kb) * nyb + yb) * d.nx + x);
+	}
+	__shared__ unsigned s_off[FLOF_BLOCK / 32], s_base;
+	const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	const unsigned b = __ballot_sync(0xffffffffu, mask != 0);
+	if (lane == 0) s_off[wid] = __popc(b);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned tot = 0;
+		for (int w = 0; w < FLOF_BLOCK / 32; ++w) {
+			const unsigned c = s_off[w];
+			s_off[w] = tot;
+			tot += c;
+		}
+		s_base = tot ? atomicAdd(count, tot) : 0u;
+	}
+	__syncthreads();
+	if (mask) items[s_base + s_off[wid] + __popc(b & ((1u << lane) - 1u))] = make_uint2(id, mask);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(FLOF_BLOCK, MINB)
+    k_cv_expol_items_z2(const float4 *__restrict__ a, float4 *__restrict__ out, const uint2 *__restrict__ items, int n,
+                        flof_kd d, int nyb)
+{
+	const int q = (int)(blockIdx.x * FLOF_BLOCK + threadIdx.x);
+	if (q >= n) return;
+	const uint2 it = __ldg(items + q);
+	const unsigned mask = it.y;
+	unsigned id = it.x;
+	const int nzb = (d.nz + 1) / 2;
+	const int x = (int)(id % (unsigned)d.nx);
+	id /= (unsigned)d.nx;
+	const int y0 = (int)(id % (unsigned)nyb) * FLOF_ETPY;
+	id /= (unsigned)nyb;
+	const int k0 = (int)(id % (unsigned)nzb) * 2, t = (int)(id / (unsigned)nzb) + d.t0;
+
+	p4 acc[2][FLOF_ETPY];
+#pragma unroll
+	for (int zo = 0; zo < 2; ++zo)
+#pragma unroll
+		for (int oy = 0; oy < FLOF_ETPY; ++oy) acc[zo][oy] = p4_zero();
+	int roff[FLOF_ETPY + 2];  // offset of (x, clamp(y0-1+r)) inside a z-t plane; clamped rows only feed unneeded outputs
+#pragma unroll
+	for (int r = 0; r < FLOF_ETPY + 2; ++r) roff[r] = min(max(y0 - 1 + r, 0), d.ny - 1) * d.nx + x;
+	const int64_t sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
+#pragma unroll 1
+	for (int vt = t - 1; vt <= t + 1; ++vt) {
+#pragma unroll 1
+		for (int pz = 0; pz < 4; ++pz) {
+			// plane k0 - 1 + pz (clamped: out-of-range planes only feed outputs on the z border, which are never needed)
+			const float4 *base = a + (sT * vt + sZ * min(max(k0 - 1 + pz, 0), d.nz - 1));
+			p4 L[FLOF_ETPY + 2][3];
+#pragma unroll
+			for (int r = 0; r < FLOF_ETPY + 2; ++r) {
+				const float4 *row = base + roff[r];
+				L[r][0] = p4_load(row - 1);
+				L[r][1] = p4_load(row);
+				L[r][2] = p4_load(row + 1);
+			}
+#pragma unroll
+			for (int zo = 0; zo < 2; ++zo) {
+				if (pz < zo || pz > zo + 2) continue;  // (uniform: pz is the loop counter)
+#pragma unroll
+				for (int r = 0; r < FLOF_ETPY + 2; ++r)
+#pragma unroll
+					for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+						if (r < oy || r > oy + 2) continue;
+						acc4(acc[zo][oy], L[r][0]);
+						acc4(acc[zo][oy], L[r][1]);
+						acc4(acc[zo][oy], L[r][2]);
+					}
+			}
+		}
+	}
+	const double f = 1. / 81.0;
+#pragma unroll
+	for (int zo = 0; zo < 2; ++zo) {
+		float4 *o = out + (sT * t + sZ * (k0 + zo) + (int64_t)y0 * d.nx + x);
+#pragma unroll
+		for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+			if (!((mask >> (zo * FLOF_ETPY + oy)) & 1u)) continue;
+			const float4 v = p4_unpack(acc[zo][oy]);
+			o[(int64_t)oy * d.nx] = make_float4((float)(v.x * f), (float)(v.y * f), (float)(v.z * f), (float)(v.w * f));
+		}
+	}
+}
+
+static int64_t flof_expol_z2_capacity(const flof_ctx *ctx, flof_dim4 d)
+{
+	int ta, tb;
+	flof_slab(ctx, d.nt, &ta, &tb);
+	const int64_t n = (int64_t)d.nx * ((d.ny + FLOF_ETPY - 1) / FLOF_ETPY) * ((d.nz + 1) / 2) * (tb - ta);
+	return n < ((int64_t)1 << 31) ? n : 0;
+}
+static int flof_expol_z2_build(flof_ctx *ctx, const float *marker, flof_dim4 d, uint2 *items, unsigned int *count, int *n)
+{
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
+	const int nyb = (d.ny + FLOF_ETPY - 1) / FLOF_ETPY;
+	g.x = (unsigned)(((int64_t)d.nx * nyb + FLOF_BLOCK - 1) / FLOF_BLOCK);
+	g.y = (unsigned)((d.nz + 1) / 2);
+	FLOF_CK(cudaMemsetAsync(count, 0, sizeof(unsigned int), ctx->stream));
+	FLOF_LAUNCH(k_expol_build_items_z2, g, FLOF_BLOCK, 0, marker, items, count, kd, nyb);
+	unsigned int *h = (unsigned int *)ctx->pinned;
+	FLOF_CK(cudaMemcpyAsync(h, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+	FLOF_CK(cudaStreamSynchronize(ctx->stream));
+	*n = (int)h[0];
+	return FLOF_OK;
+}
+static int flof_launch_expol_z2(flof_ctx *ctx, const float *a, float *out, const uint2 *items, int n, flof_dim4 d)
+{
+	if (n <= 0) return FLOF_OK;
+	dim3 g;
+	const flof_kd kd = flof_kdim(ctx, d, &g);
+	const int nyb = (d.ny + FLOF_ETPY - 1) / FLOF_ETPY;
+	const dim3 gi((unsigned)((n + FLOF_BLOCK - 1) / FLOF_BLOCK));
+	if (ctx->opt.expol_variant == 1)
+		FLOF_LAUNCH((k_cv_expol_items_z2<1>), gi, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)out, items, n, kd, nyb);
+	else
+		FLOF_LAUNCH((k_cv_expol_items_z2<2>), gi, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)out, items, n, kd, nyb);
+	return FLOF_OK;
+}
+
 // ------------------------------------------------------------------ 81-tap extrapolation, component planes ---
 // The work-list kernel above is bound by the L1 data pipe: 162 LDG.128 per item feed 648 packed adds, and every
 // row costs three requests (x-1, x, x+1) that re-read the same lines (ncu: l1tex data-pipe 87 %, fma pipe 27 %).

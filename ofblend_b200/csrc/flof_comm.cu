@@ -200,9 +200,7 @@ static void flof_p2p_release(flof_ctx *ctx)
 // (re)allocates the mailboxes so that one halo buffer holds `need` bytes; collective over all ranks
 int flof_p2p_ensure(flof_ctx *ctx, size_t need)
 {
-	static int disabled = -1;
-	if (disabled < 0) disabled = getenv("FLOF_NO_P2P") ? 1 : 0;
-	if (disabled || ctx->nranks > FLOF_P2P_MAX) return FLOF_OK;
+	if (ctx->opt.no_p2p || ctx->nranks > FLOF_P2P_MAX) return FLOF_OK;  // "no_p2p": flof_ctx_set_option / FLOF_NO_P2P
 	if (ctx->p2p.enabled && need <= ctx->p2p.cap) return FLOF_OK;
 	if (ctx->p2p.mbox) flof_p2p_release(ctx);
 	FLOF_CK(cudaStreamSynchronize(ctx->stream));
@@ -255,7 +253,7 @@ int flof_p2p_ensure(flof_ctx *ctx, size_t need)
 	ctx->p2p.cap = cap;
 	ctx->p2p.halo_seq = 0;
 	ctx->p2p.enabled = ok;
-	if (!ok) disabled = 1;
+	if (!ok) ctx->opt.no_p2p = 1;  // a mapping failed on some rank (agreed by all-reduce above): NCCL from now on
 	return FLOF_OK;
 }
 

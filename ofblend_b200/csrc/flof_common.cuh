@@ -40,6 +40,7 @@ struct flof_cg_state {
 	int iter;          // completed iterations
 	int done;          // 1 = stop (converged, early-out or failed)
 	int status;        // 0 running, 1 converged, 2 early-out residual0 < eps, 3 sigma == 0 / NaN
+	int seq_inexact;   // a sequential-order dot product exceeded its capacities on a range too large for the plain loop
 };
 
 // ---- NVLink peer mailboxes (flof_comm.cu): every rank owns one cudaMalloc'ed, IPC-exported buffer that all
@@ -106,7 +107,8 @@ struct flof_ctx {
 	struct {
 		int expol_mode;     // 1 Vec4 work list (default), 0 component planes, 2 dense kernel
 		int expol_variant;  // register budget / unrolling variant of the chosen extrapolation kernel
-		int apply_variant;  // CG apply: 7 (default) = streaming hints + 8 CTAs/SM (32 registers); 0 plain, 1..6 other occupancy points
+		int apply_variant;  // CG apply: 11 (default) = streaming hints + 6 CTAs/SM (40 registers, no spills); 7 = 8 CTAs/SM; 0, 1, 3, 5, 9, 10 other occupancy / unrolling points
+		int no_p2p;         // 1: keep NCCL for halos and CG scalars (no NVLink peer mailboxes; tree-order dot products)
 		int dot_mode;       // CG dot products: 1 (default) = the reference's sequential summation order, bit for bit
 		                    // (flof_seqsum); 0 = tree reductions (faster, last bits of the fp64 sums differ)
 	} opt;

@@ -74,12 +74,15 @@ __global__ void __launch_bounds__(FLOF_BLOCK) k_extrap_first_ring(int *tmp, flof
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t) || !flof_in_bounds(d, i, j, k, t, 1)) return;
 	const int64_t c = flof_idx(d, i, j, k, t);
-	if (tmp[c]) return;
+	// In-place update: neighbours are read while other threads may store a 2 into them.  A concurrently written 2 never
+	// equals 1, so the outcome does not depend on the interleaving; the accesses are volatile (single, untorn 32-bit
+	// loads / stores the compiler may neither cache nor split), which makes that argument hold formally as well.
+	volatile int *vt = tmp;
+	if (vt[c]) return;
 	const int64_t sY = d.nx, sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
-	// a concurrently written 2 never equals 1, so reading neighbours in place is safe
-	if (tmp[c - 1] == 1 || tmp[c + 1] == 1 || tmp[c - sY] == 1 || tmp[c + sY] == 1 || tmp[c - sZ] == 1 ||
-	    tmp[c + sZ] == 1 || tmp[c - sT] == 1 || tmp[c + sT] == 1)
-		tmp[c] = 2;
+	if (vt[c - 1] == 1 || vt[c + 1] == 1 || vt[c - sY] == 1 || vt[c + sY] == 1 || vt[c - sZ] == 1 ||
+	    vt[c + sZ] == 1 || vt[c - sT] == 1 || vt[c + sT] == 1)
+		vt[c] = 2;
 }
 // ref knExtrap4dLsSimple :1330-1352; neighbour order nbs4d: -x,+x,-y,+y,-z,+z,-t,+t
 template <class T>
@@ -89,7 +92,11 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t) || !flof_in_bounds(d, i, j, k, t, 1)) return;
 	const int64_t c = flof_idx(d, i, j, k, t);
-	if (tmp[c] != 0) return;
+	// In-place sweep (like the reference's kernel): only cells with marker 0 are written (marker dd + 1, new value), only
+	// neighbours with marker == dd are read -- those are not written in this sweep, and a concurrently stored dd + 1
+	// never equals dd.  Marker accesses are volatile (untorn 32-bit loads / stores) so this holds formally.
+	volatile int *vt = tmp;
+	if (vt[c] != 0) return;
 	const int64_t sY = d.nx, sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
 	const int64_t o[8] = { -1, 1, -sY, sY, -sZ, sZ, -sT, sT };
 	int nbs = 0;
@@ -97,14 +104,14 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	if constexpr (sizeof(T) == 4) avg = 0.f; else avg = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
 	for (int n = 0; n < 8; ++n) {
-		if (tmp[c + o[n]] == dd) {
+		if (vt[c + o[n]] == dd) {
 			const T q = val[c + o[n]];
 			if constexpr (sizeof(T) == 4) { avg += q; } else { avg.x += q.x; avg.y += q.y; avg.z += q.z; avg.w += q.w; }
 			nbs++;
 		}
 	}
 	if (nbs > 0) {
-		tmp[c] = dd + 1;
+		vt[c] = dd + 1;
 		const float fn = (float)nbs;  // avg / nbs: int promoted to float
 		if constexpr (sizeof(T) == 4) {
 			val[c] = avg / fn + direction;

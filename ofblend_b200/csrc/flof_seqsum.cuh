@@ -21,11 +21,12 @@
 #define SEQ_U 4                              // cells per thread and leaf
 #define SEQ_LEAF_CELLS (FLOF_BLOCK * SEQ_U)  // 1024 cells = 4096 products per leaf
 #define SEQ_CHUNK_CELLS 128                  // fast path: cells a warp folds per step (4 per lane)
-#define SEQ_ECAP 64                          // entries a segment may emit (fast path: 1)
+#define SEQ_ECAP 520                         // entries a segment may emit (fast path: 1)
 #define SEQ_DMAX 1024                        // dirty leaves the resolver can take per dot product
 #define SEQ_POOL (1 << 18)                   // pieces (32 B each) all dirty leaves of one dot product may use
-#define SEQ_PIECE_SMEM 1024                  // pieces the resolver stages in shared memory
-#define SEQ_EMAX 3072                        // segment entries the resolver stages in shared memory
+#define SEQ_STAGE 1536                       // pieces of ONE dirty leaf (k_dot_seq stages them in shared memory)
+#define SEQ_EMAX 2560                        // segment entries the resolver stages in shared memory
+#define SEQ_MAX_SEG 2048                     // segments per rank
 #define SEQ_PLAIN_MAX (1 << 21)                // cells up to which the resolver's fallback is the plain one-thread loop
 #define SEQ_SA_SLACK 1.001                   // the producers sum |product| in fp32: inflate to a rigorous upper bound
 
@@ -39,12 +40,17 @@ struct seq_part {
 struct seq_seg {  // per segment: approximate sum / magnitude bound of the segment and of everything before it in the range
 	double sx, sa, px, pa;
 };
+struct seq_cls {  // classification of a segment by the tail of pass 1
+	int mode;     // SEQ_LEAF_WILD (all zero) / SEQ_LEAF_CLEAN (safe: one binade) / SEQ_LEAF_DIRTY (careful path)
+	int e;        // binade of a safe segment
+};
 
 struct seq_ctl {  // device-resident control block of one context
+	unsigned int ticket;       // next entry of the work list (k_dot_seq), reset by the resolver
 	unsigned int ndirty;       // dirty leaves of the running dot product
 	unsigned int pool_used;    // pieces allocated from the pool
-	unsigned int flags;        // bit 0: non-finite product seen, bit 1: capacity exceeded, bit 2: consistency check failed
-	unsigned int pad;
+	unsigned int flags;        // bit 0: non-finite product seen, bit 1: capacity exceeded (bits 8..12: which), bit 2: consistency check failed
+	unsigned int why;          // OR of the flags of every fallback since context creation
 	double result;             // last resolved sum (exact bits of the sequential loop)
 	double tot[2];             // approximate sum / magnitude bound of this rank's range (tail of pass 1)
 	double off[2];             // the same for all lower ranks together (0 on a single GPU)
@@ -52,33 +58,26 @@ struct seq_ctl {  // device-resident control block of one context
 };
 
 struct flof_seq {  // host-side handle (ctx->seq)
-	seq_seg *seg;      // [FLOF_MAX_PARTIALS]
-	seq_rec *ent;      // [FLOF_MAX_PARTIALS * SEQ_ECAP] entries of the segments, in order
-	int *ecnt;         // [FLOF_MAX_PARTIALS]
-	double *aggx, *agga;  // [FLOF_MAX_PARTIALS] each: segment accumulators of the stencil kernel (atomics)
+	seq_seg *seg;      // [SEQ_MAX_SEG]
+	seq_cls *cls;      // [SEQ_MAX_SEG]
+	int *order;        // [SEQ_MAX_SEG] work list of pass 2: careful segments first (they take longest), then the safe ones
+	seq_rec *ent;      // [SEQ_MAX_SEG * SEQ_ECAP] entries of the segments, in order
+	int *ecnt;         // [SEQ_MAX_SEG]
+	double *aggx, *agga;  // [SEQ_MAX_SEG] each: per-segment sums of pass 1 (plain stores, or atomics of the stencil kernel); zero between launches
 	seq_rec *pool;     // [SEQ_POOL]
 	seq_ctl *ctl;
 };
 
-// host: segment size for a range of `ncells` cells; slice_cells = cells of one t-slice (0 if unknown).  A segment count
-// near per_sm CTAs per SM (the occupancy of the stencil kernel) keeps every producing CTA resident at once; segments that tile a t-slice make the t-1 / t+1
-// neighbours of the stencil kernel the CENTRE cells of another resident CTA at the same moment (synchronised streaming).
-static inline seq_part seq_make_part(int64_t ncells, int64_t slice_cells, int sm_count, int per_sm = 8)
+// host: segment size for a range of `ncells` cells; slice_cells = cells of one t-slice (0 if unknown).  About SEQ_MAX_SEG
+// segments: fine enough for the dynamic scheduling of pass 2, few enough for the one-CTA tail scan and the resolver.
+static inline seq_part seq_make_part(int64_t ncells, int64_t slice_cells, int sm_count)
 {
+	(void)slice_cells;
+	(void)sm_count;
 	seq_part p;
 	const int64_t leaves = (ncells + SEQ_LEAF_CELLS - 1) / SEQ_LEAF_CELLS;
-	int64_t cap = (int64_t)sm_count * per_sm;
-	if (cap > FLOF_MAX_PARTIALS) cap = FLOF_MAX_PARTIALS;
-	int64_t R = (leaves + cap - 1) / cap;
+	int64_t R = (leaves + SEQ_MAX_SEG - 1) / SEQ_MAX_SEG;
 	if (R < 1) R = 1;
-	if (slice_cells > 0 && slice_cells % SEQ_LEAF_CELLS == 0) {
-		const int64_t lps = slice_cells / SEQ_LEAF_CELLS;
-		for (int64_t r = R; r <= 2 * R && r <= lps; ++r)
-			if (lps % r == 0) {
-				R = r;
-				break;
-			}
-	}
 	p.ncells = (int)ncells;
 	p.seg_cells = (int)(R * SEQ_LEAF_CELLS);
 	p.nseg = (int)((leaves + R - 1) / R);

@@ -124,10 +124,11 @@ SEQ_HD seq_fn seq_compose(const seq_fn &f, const seq_fn &g)
 // S <- f(S); S must lie in the function's binade (checked by the caller)
 SEQ_HD double seq_apply(double S, const seq_fn &f) { return S + ((seq_bits(S) & 1ull) ? f.d1 : f.d0); }
 
-// error margin of an approximate prefix: |approx - sequential fp64 sum| <= Kf * (sum of |x| so far).
-// Sequential summation of k terms is off the real sum by at most k * 2^-53 * sum|x| (1 + ...); the approximate
-// prefix (arbitrary tree order) by far less.  Factor 2 and 2^20 extra terms of slack.
-SEQ_HD double seq_margin_factor(int64_t n_total) { return 2.0 * ((double)n_total + 1048576.0) * 1.1102230246251565e-16; }
+// error margin of an approximate prefix after n products: |approx - sequential fp64 sum| <= Kf * (sum of |x| so far).
+// Sequential summation of n terms is off the real sum by at most gamma_(n-1) * sum|x|, gamma_k = k u / (1 - k u),
+// u = 2^-53; the approximate prefix (per-thread partial sums of <= 2^13 terms combined by trees) by less than 2^14 u sum|x|.
+// (n + 2^20) u covers both for every n < 2^32: n u * n u < 2^20 u.
+SEQ_HD double seq_margin_factor(int64_t n) { return ((double)n + 1048576.0) * 1.1102230246251565e-16; }
 
 // Is a range of products (sum of magnitudes sa) whose running sum starts near P (approximate, |error| <= m)
 // guaranteed to stay inside binade(P), with every product small enough for seq_elem?

@@ -24,13 +24,21 @@
 
 struct seq_args {
 	seq_seg *seg;
+	seq_cls *cls;
+	int *order;
+	double *aggx, *agga;
 	seq_rec *ent;
 	int *ecnt;
 	seq_rec *pool;
 	seq_ctl *ctl;
 	seq_part part;
-	double kf;  // seq_margin_factor(total number of products over all ranks)
+	int64_t n0;  // products of the lower ranks' ranges (0 on a single GPU): global position of this range in the sum
 };
+// margin factor for everything up to the end of segment `seg` (the bound grows with the number of terms summed so far)
+__device__ __forceinline__ double seq_kf_of(const seq_args &A, int seg)
+{
+	return seq_margin_factor(A.n0 + 4ll * min((int64_t)(seg + 1) * A.part.seg_cells, (int64_t)A.part.ncells));
+}
 
 #define SEQ_MODE_NONE 0     // result only (seq_ctl::result)
 #define SEQ_MODE_ALPHA 1    // st->alpha1 = dot(srch, A srch)                  ref :307
@@ -159,32 +167,71 @@ __device__ __forceinline__ void seq_block_sum2(double &x, double &y, double *sh)
 	}
 }
 
-// ---- pass 1 tail (ONE block, every thread): per-segment partials -> exclusive prefixes within this rank's range.
-// px[b] / pa[b]: approximate sum of the products of segment b / fp32-accumulated sum of their magnitudes.
-// totals (thread 0 only): tx, ta (ta already carries SEQ_SA_SLACK).
-__device__ __forceinline__ void seq_tail_scan(seq_seg *seg, int nseg, const double *px, const double *pa, double *sh, double &tx,
-                                              double &ta)
+// ---- pass 1 tail (ONE block, every thread): per-segment sums -> exclusive prefixes within this rank's range.
+// aggx[b] / agga[b]: approximate sum of the products of segment b / fp32-accumulated sum of their magnitudes; both are
+// zeroed for the next launch.  totals (every thread): tx, ta (ta already carries SEQ_SA_SLACK).
+__device__ __forceinline__ void seq_tail_scan(const seq_args &A, double *sh, double &tx, double &ta)
 {
+	const int nseg = A.part.nseg;
 	const int per = (nseg + FLOF_BLOCK - 1) / FLOF_BLOCK;  // <= 8
 	const int b0 = min((int)threadIdx.x * per, nseg), b1 = min(b0 + per, nseg);
 	double lx = 0., la = 0.;
 	for (int b = b0; b < b1; ++b) {
-		lx += px[b];
-		la += pa[b];
+		lx += A.aggx[b];
+		la += A.agga[b];
 	}
 	double ex = lx, ea = la;
 	seq_block_exscan2(ex, ea, sh, tx, ta);
 	for (int b = b0; b < b1; ++b) {
+		const double vx = A.aggx[b], va = A.agga[b];
 		seq_seg s;
-		s.sx = px[b];
-		s.sa = pa[b] * SEQ_SA_SLACK;
+		s.sx = vx;
+		s.sa = va * SEQ_SA_SLACK;
 		s.px = ex;
 		s.pa = ea * SEQ_SA_SLACK;
-		seg[b] = s;
-		ex += px[b];
-		ea += pa[b];
+		A.seg[b] = s;
+		ex += vx;
+		ea += va;
+		A.aggx[b] = 0.;
+		A.agga[b] = 0.;
 	}
 	ta *= SEQ_SA_SLACK;
+}
+// ---- then (the lower ranks' share offx / offa known): classify every segment and build the work list of pass 2,
+// careful segments first.  shi: >= 8 ints.
+__device__ __forceinline__ void seq_tail_classify(const seq_args &A, double offx, double offa, int *shi)
+{
+	const int nseg = A.part.nseg;
+	const int per = (nseg + FLOF_BLOCK - 1) / FLOF_BLOCK;
+	const int b0 = min((int)threadIdx.x * per, nseg), b1 = min(b0 + per, nseg);
+	int ncare = 0;
+	unsigned bits = 0;
+	for (int b = b0; b < b1; ++b) {
+		const seq_seg s = A.seg[b];
+		const double P = offx + s.px, T = offa + s.pa;
+		seq_cls c;
+		c.e = 0;
+		if (!seq_finite(s.sx) || !seq_finite(s.sa) || !seq_finite(P) || !seq_finite(T)) {
+			atomicOr(&A.ctl->flags, 1u);
+			c.mode = SEQ_LEAF_WILD;
+		} else if (s.sa == 0.)
+			c.mode = SEQ_LEAF_WILD;
+		else
+			c.mode = seq_range_safe(P, T, s.sa, seq_kf_of(A, b), &c.e) ? SEQ_LEAF_CLEAN : SEQ_LEAF_DIRTY;
+		A.cls[b] = c;
+		if (c.mode == SEQ_LEAF_DIRTY) {
+			++ncare;
+			bits |= 1u << (b - b0);
+		}
+	}
+	int total;
+	int before = seq_block_exscan_int(ncare, shi, total);
+	for (int b = b0; b < b1; ++b) {
+		if ((bits >> (b - b0)) & 1u)
+			A.order[before++] = b;
+		else
+			A.order[total + b - before] = b;  // safe / empty segments keep their order behind the careful ones
+	}
 }
 
 // stand-alone pass 1: one CTA per segment
@@ -193,6 +240,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
     k_seq_agg(const float4 *__restrict__ a, const float4 *__restrict__ b, float diag, seq_args A, flof_reduce_scratch *red)
 {
 	__shared__ double shd[32];
+	__shared__ int shi[8];
 	const int seg = blockIdx.x;
 	const int c0 = seg * A.part.seg_cells, c1 = min(c0 + A.part.seg_cells, A.part.ncells);
 	double sx = 0.;
@@ -205,12 +253,14 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	double sa = (double)af;
 	seq_block_sum2(sx, sa, shd);
 	if (threadIdx.x == 0) {
-		red->dsum[0][seg] = sx;
-		red->asum[seg] = sa;
+		A.aggx[seg] = sx;
+		A.agga[seg] = sa;
 	}
 	if (flof_last_block(&red->counter[1])) {
 		double tx, ta;
-		seq_tail_scan(A.seg, A.part.nseg, red->dsum[0], red->asum, shd, tx, ta);
+		seq_tail_scan(A, shd, tx, ta);
+		__syncthreads();
+		seq_tail_classify(A, 0., 0., shi);
 		if (threadIdx.x == 0) {
 			A.ctl->tot[0] = tx;
 			A.ctl->tot[1] = ta;
@@ -253,7 +303,7 @@ struct seq_builder {  // consecutive safe products of one binade merge into one 
 		} else {
 			flush();
 			seq_rec r;
-			r.d0 = x; r.d1 = 0.; r.e = SEQ_E_RAW; r.q = 0; r.pad[0] = r.pad[1] = 0;
+			r.d0 = x; r.d1 = x; r.e = SEQ_E_RAW; r.q = 0; r.pad[0] = r.pad[1] = 0;  // (d1 = d0: the walk adds by parity)
 			out[n++] = r;
 		}
 	}
@@ -272,7 +322,7 @@ struct seq_emitter {
 		if (n < SEQ_ECAP)
 			out[n] = r;
 		else
-			atomicOr(flags, 2u);
+			atomicOr(flags, 2u | 0x100u);   // segment entry list full
 		++n;
 	}
 	__device__ __forceinline__ void flush()
@@ -301,14 +351,19 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
     k_dot_seq(const float4 *__restrict__ a, const float4 *__restrict__ b, float diag, seq_args A, const flof_cg_state *st)
 {
 	if (st && st->done) return;
-	__shared__ __align__(16) float s_x[FLOF_BLOCK * SEQ_XS];  // 20 KB: eight warp tiles / one leaf / piece staging
+	extern __shared__ __align__(16) float s_x[];  // SEQ_DOT_SMEM: eight warp tiles / one leaf (20 KB) / piece staging (48 KB)
 	__shared__ double shd[32];
 	__shared__ seq_fn s_fn[FLOF_BLOCK / 32];
 	__shared__ int shi[8], s_wb[8];
-	__shared__ int s_mode, s_e;
+	__shared__ int s_mode, s_e, s_seg;
 	__shared__ double s_P, s_T;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	for (int seg = blockIdx.x; seg < A.part.nseg; seg += gridDim.x) {
+	for (;;) {
+		// work list of the tail of pass 1: careful segments first, handed out by ticket
+		if (tid == 0) s_seg = (int)atomicAdd(&A.ctl->ticket, 1u);
+		__syncthreads();
+		if (s_seg >= A.part.nseg) break;
+		const int seg = A.order[s_seg];
 		const int c0 = seg * A.part.seg_cells, c1 = min(c0 + A.part.seg_cells, A.part.ncells);
 		seq_emitter em;
 		em.out = A.ent + (size_t)seg * SEQ_ECAP; em.n = 0; em.have = false; em.e = 0; em.f = seq_identity();
@@ -316,18 +371,11 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		double P = 0., T = 0.;  // running approximate prefix (thread 0)
 		if (tid == 0) {
 			const seq_seg s = A.seg[seg];
+			const seq_cls c = A.cls[seg];
 			P = A.ctl->off[0] + s.px;
 			T = A.ctl->off[1] + s.pa;
-			int mode, e = 0;
-			if (!seq_finite(s.sx) || !seq_finite(s.sa) || !seq_finite(P) || !seq_finite(T)) {
-				atomicOr(&A.ctl->flags, 1u);
-				mode = SEQ_LEAF_WILD;
-			} else if (s.sa == 0.)
-				mode = SEQ_LEAF_WILD;
-			else
-				mode = seq_range_safe(P, T, s.sa, A.kf, &e) ? SEQ_LEAF_CLEAN : SEQ_LEAF_DIRTY;
-			s_mode = mode;
-			s_e = e;
+			s_mode = c.mode;
+			s_e = c.e;
 		}
 		__syncthreads();
 		const int smode = s_mode;
@@ -364,6 +412,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		} else if (smode == SEQ_LEAF_DIRTY) {
 			// ---- careful segment: leaf by leaf with a running prefix
 			if (tid == 0) atomicAdd(&A.ctl->n_slow_segments, 1ull);
+			const double kf = seq_kf_of(A, seg);
 			for (int l0 = c0; l0 < c1; l0 += SEQ_LEAF_CELLS) {
 				double sx = 0., sa = 0.;
 #pragma unroll
@@ -384,7 +433,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 					} else if (sa == 0.)
 						mode = SEQ_LEAF_WILD;
 					else
-						mode = seq_range_safe(P, T, sa, A.kf, &e) ? SEQ_LEAF_CLEAN : SEQ_LEAF_DIRTY;
+						mode = seq_range_safe(P, T, sa, kf, &e) ? SEQ_LEAF_CLEAN : SEQ_LEAF_DIRTY;
 					s_mode = mode;
 					s_e = e;
 					s_P = P;
@@ -428,7 +477,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 #pragma unroll 1
 					for (int k = 0; k < 4 * SEQ_U; ++k) {
 						const double x = (double)xs[k];
-						bd.push(x, Pk, Tk, A.kf);
+						bd.push(x, Pk, Tk, kf);
 						Pk += x;
 						Tk += seq_abs(x);
 					}
@@ -436,7 +485,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 					int total;
 					const int off = seq_block_exscan_int(bd.n, shi, total);
 					seq_rec *stage = reinterpret_cast<seq_rec *>(s_x);
-					const int cap = (int)(sizeof(s_x) / sizeof(seq_rec));
+					const int cap = SEQ_STAGE;
 					if (total <= cap)
 						for (int k = 0; k < bd.n; ++k) stage[off + k] = pc[k];
 					__syncthreads();
@@ -463,7 +512,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 					__syncthreads();
 					if (tid == 0) {
 						if (total > cap)
-							atomicOr(&A.ctl->flags, 2u);
+							atomicOr(&A.ctl->flags, 2u | 0x200u);  // pieces of one dirty leaf exceed the staging area
 						else {
 							int m = 0, nraw = 0;
 							for (int w = 0; w < FLOF_BLOCK / 32; ++w) {
@@ -484,7 +533,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 							const unsigned id = atomicAdd(&A.ctl->ndirty, 1u);
 							const unsigned base = atomicAdd(&A.ctl->pool_used, (unsigned)m);
 							if (id >= SEQ_DMAX || base + (unsigned)m > SEQ_POOL)
-								atomicOr(&A.ctl->flags, 2u);
+								atomicOr(&A.ctl->flags, 2u | 0x400u);  // dirty-leaf list or piece pool full
 							else {
 								for (int k = 0; k < m; ++k) A.pool[base + k] = stage[k];
 								em.flush();
@@ -508,9 +557,12 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	}
 }
 
-// dynamic shared memory of the resolver
-#define SEQ_RESOLVE_SMEM                                                                                              \
-	((size_t)(SEQ_EMAX + FLOF_BLOCK + SEQ_DMAX + SEQ_PIECE_SMEM) * sizeof(seq_rec) + (size_t)SEQ_DMAX * 2 * sizeof(int))
+#define SEQ_DOT_SMEM ((size_t)SEQ_STAGE * sizeof(seq_rec))  // >= FLOF_BLOCK * SEQ_XS floats
+
+// dynamic shared memory of the resolver: all segment entries, then the flat list of walk steps
+#define SEQ_CTHREADS 64  // threads that compose entry chunks (one run step each + their dirty leaves)
+#define SEQ_SMAX 4096    // walk steps (run steps + pieces of the dirty leaves) staged in shared memory
+#define SEQ_RESOLVE_SMEM ((size_t)(SEQ_EMAX + SEQ_SMAX) * sizeof(seq_rec) + (size_t)SEQ_DMAX * 3 * sizeof(int))
 
 template <int KIND>
 __global__ void __launch_bounds__(FLOF_BLOCK)
@@ -520,42 +572,46 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	if (st && st->done) return;
 	extern __shared__ __align__(16) unsigned char seq_smem[];
 	seq_rec *s_in = reinterpret_cast<seq_rec *>(seq_smem);       // [SEQ_EMAX] all segment entries, in order
-	seq_rec *s_ent = s_in + SEQ_EMAX;                            // [FLOF_BLOCK + SEQ_DMAX] composed runs between dirty leaves
-	seq_rec *s_pc = s_ent + FLOF_BLOCK + SEQ_DMAX;               // [SEQ_PIECE_SMEM] staged pieces of the dirty leaves
-	int *s_de = reinterpret_cast<int *>(s_pc + SEQ_PIECE_SMEM);  // [SEQ_DMAX] entry index of dirty leaf k (in order)
-	int *s_po = s_de + SEQ_DMAX;                                 // offset of its pieces in s_pc, -1 = read from the pool
+	seq_rec *s_st = s_in + SEQ_EMAX;                             // [SEQ_SMAX] walk steps, in order
+	int *s_jsrc = reinterpret_cast<int *>(s_st + SEQ_SMAX);      // [SEQ_DMAX] copy jobs of the dirty leaves: pool offset,
+	int *s_jcnt = s_jsrc + SEQ_DMAX;                             //            piece count,
+	int *s_jdst = s_jcnt + SEQ_DMAX;                             //            first step
 	__shared__ int shi[8];
 	__shared__ unsigned s_bad;
-	__shared__ int s_E, s_D;
+	__shared__ int s_E, s_D, s_N;
 	const int tid = threadIdx.x;
 	seq_ctl *ctl = A.ctl;
 	const unsigned flags = ctl->flags;
 	const int nseg = A.part.nseg;
-	if (tid == 0) s_bad = (flags & 6u) | (ctl->ndirty > SEQ_DMAX ? 2u : 0u);
+	if (tid == 0) s_bad = (flags & ~1u) | (ctl->ndirty > SEQ_DMAX ? 2u | 0x400u : 0u);
 	// ---- A: gather the segment entries in order
 	{
 		const int per = (nseg + FLOF_BLOCK - 1) / FLOF_BLOCK;
 		const int b0 = min(tid * per, nseg), b1 = min(b0 + per, nseg);
-		int sum = 0;
-		for (int s = b0; s < b1; ++s) sum += A.ecnt[s];
+		int cnt[8], sum = 0;  // per <= 8 (SEQ_MAX_SEG / FLOF_BLOCK)
+#pragma unroll
+		for (int q = 0; q < 8; ++q) {
+			cnt[q] = b0 + q < b1 ? A.ecnt[b0 + q] : 0;
+			sum += cnt[q];
+		}
 		int total;
 		int off = seq_block_exscan_int(sum, shi, total);
 		if (tid == 0) s_E = total;
-		if (total <= SEQ_EMAX)
-			for (int s = b0; s < b1; ++s) {
-				const int n = A.ecnt[s];
-				for (int k = 0; k < n; ++k) s_in[off + k] = A.ent[(size_t)s * SEQ_ECAP + k];
-				off += n;
+		if (total <= SEQ_EMAX) {
+#pragma unroll
+			for (int q = 0; q < 8; ++q) {
+				for (int k = 0; k < cnt[q]; ++k) s_in[off + k] = A.ent[(size_t)(b0 + q) * SEQ_ECAP + k];
+				off += cnt[q];
 			}
-		else if (tid == 0)
-			atomicOr(&s_bad, 2u);
+		} else if (tid == 0)
+			atomicOr(&s_bad, 2u | 0x800u);  // more segment entries than the resolver stages
 	}
 	__syncthreads();
 	const int E = s_E <= SEQ_EMAX ? s_E : 0;
-	const int chunk = (E + FLOF_BLOCK - 1) / FLOF_BLOCK;
-	const int e0 = min(tid * chunk, E), e1 = min(e0 + chunk, E);
-	// ---- B: the dirty leaves (already in order), their pieces staged in shared memory
-	int dbefore;
+	// ---- B: SEQ_CTHREADS threads own consecutive chunks of entries: dirty leaves and pieces per chunk -> step offsets
+	const int chunk = (E + SEQ_CTHREADS - 1) / SEQ_CTHREADS;
+	const int e0 = tid < SEQ_CTHREADS ? min(tid * chunk, E) : E, e1 = tid < SEQ_CTHREADS ? min(e0 + chunk, E) : E;
+	int dbefore, pbefore;
 	{
 		int nd = 0, np = 0;
 		for (int k = e0; k < e1; ++k)
@@ -565,34 +621,20 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 			}
 		int D, NP;
 		dbefore = seq_block_exscan_int(nd, shi, D);
-		int poff = seq_block_exscan_int(np, shi, NP);
-		if (tid == 0) s_D = D;
-		if (D <= SEQ_DMAX) {
-			int dk = dbefore;
-			for (int k = e0; k < e1; ++k)
-				if (s_in[k].e == SEQ_E_DIRTY) {
-					const int n = s_in[k].pad[1];
-					s_de[dk] = k;
-					s_po[dk] = poff + n <= SEQ_PIECE_SMEM ? poff : -1;
-					poff += n;
-					++dk;
-				}
-		} else if (tid == 0)
-			atomicOr(&s_bad, 2u);
+		pbefore = seq_block_exscan_int(np, shi, NP);
+		if (tid == 0) {
+			s_D = D;
+			s_N = SEQ_CTHREADS + D + NP;
+			if (D > SEQ_DMAX || SEQ_CTHREADS + D + NP > SEQ_SMAX) atomicOr(&s_bad, 2u | 0x1000u);  // more dirty leaves / walk steps than the resolver stages
+		}
 	}
 	__syncthreads();
-	const int D = s_D <= SEQ_DMAX ? s_D : 0;
-	for (int k = tid >> 5; k < D; k += FLOF_BLOCK / 32) {  // one warp per dirty leaf, lanes over its pieces
-		const int po = s_po[k];
-		if (po < 0) continue;
-		const seq_rec d = s_in[s_de[k]];
-		const seq_rec *src = A.pool + d.pad[0];
-		for (int j = tid & 31; j < d.pad[1]; j += 32) s_pc[po + j] = src[j];
-	}
-	// ---- C: every thread composes the runs of its chunk of entries, cutting at dirty leaves.
-	// Slot of thread t = t + (dirty leaves before its chunk) + (dirty leaves met so far): dense and ordered.
-	{
-		int slot = tid + dbefore, dk = dbefore;
+	const bool fits = s_D <= SEQ_DMAX && s_N <= SEQ_SMAX;
+	const int D = fits ? s_D : 0, N = fits ? s_N : 0;
+	// ---- C: every composing thread folds the runs of its chunk into run steps, cutting at dirty leaves.
+	// First step of thread t = t + (dirty leaves before its chunk) + (their pieces): dense and ordered.
+	if (tid < SEQ_CTHREADS && fits) {
+		int pos = tid + dbefore + pbefore, dk = dbefore;
 		seq_fn f = seq_identity();
 		int e = SEQ_E_WILD;
 		unsigned bad = 0;
@@ -601,8 +643,12 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 			if (r.e == SEQ_E_WILD) continue;
 			if (r.e == SEQ_E_DIRTY) {
 				seq_rec o;
-				o.d0 = f.d0; o.d1 = f.d1; o.e = e; o.q = f.q; o.pad[0] = dk; o.pad[1] = 0;
-				s_ent[slot++] = o;
+				o.d0 = f.d0; o.d1 = f.d1; o.e = e; o.q = f.q; o.pad[0] = o.pad[1] = 0;
+				s_st[pos++] = o;
+				s_jsrc[dk] = r.pad[0];
+				s_jcnt[dk] = r.pad[1];
+				s_jdst[dk] = pos;
+				pos += r.pad[1];
 				++dk;
 				f = seq_identity();
 				e = SEQ_E_WILD;
@@ -614,13 +660,20 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 			f = seq_compose(f, g);
 		}
 		seq_rec o;
-		o.d0 = f.d0; o.d1 = f.d1; o.e = e; o.q = f.q; o.pad[0] = -1; o.pad[1] = 0;
-		s_ent[slot] = o;
+		o.d0 = f.d0; o.d1 = f.d1; o.e = e; o.q = f.q; o.pad[0] = o.pad[1] = 0;
+		s_st[pos] = o;
 		if (bad) atomicOr(&s_bad, bad);
 	}
 	__syncthreads();
+	for (int k = tid >> 5; k < D; k += FLOF_BLOCK / 32) {  // one warp per dirty leaf copies its pieces into place
+		const seq_rec *src = A.pool + s_jsrc[k];
+		seq_rec *dst = s_st + s_jdst[k];
+		for (int j = tid & 31; j < s_jcnt[k]; j += 32) dst[j] = src[j];
+	}
+	__syncthreads();
 	if (tid != 0) return;
-	// ---- D: the sequential walk
+	// ---- D: the sequential walk (one thread).  A step adds d0 / d1 by the parity of the running sum's mantissa; raw
+	// products carry d0 = d1 = the product, identity steps zeros -- one select + one fp64 add per step on the critical path
 	double S = 0.;
 	unsigned int cseq = 0;
 	if (multi) {  // the running sum continues from the rank below (exact bits handed over through the mailboxes)
@@ -635,31 +688,15 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		// a non-finite product: every summation order ends in the same Inf/NaN class; take the approximate sum
 		S = S + ctl->tot[0];
 	} else if (!bad) {
-		const int nent = FLOF_BLOCK + D;
-		for (int k = 0; k < nent && !bad; ++k) {
-			const seq_rec r = s_ent[k];
-			if (r.e != SEQ_E_WILD) {
-				if (seq_binade(S) != r.e) { bad = 4u; break; }
-				const seq_fn f = { r.d0, r.d1, r.q };
-				S = seq_apply(S, f);
-			}
-			const int dk = r.pad[0];
-			if (dk >= 0) {
-				const seq_rec d = s_in[s_de[dk]];
-				const int cnt = d.pad[1];
-				const seq_rec *pc = s_po[dk] >= 0 ? s_pc + s_po[dk] : A.pool + d.pad[0];
-				for (int j = 0; j < cnt; ++j) {
-					const seq_rec q = pc[j];
-					if (q.e == SEQ_E_RAW)
-						S = __dadd_rn(S, q.d0);
-					else {
-						if (seq_binade(S) != q.e) { bad = 4u; break; }
-						const seq_fn f = { q.d0, q.d1, q.q };
-						S = seq_apply(S, f);
-					}
-				}
-			}
+		unsigned wrong = 0;
+		seq_rec r = s_st[0];
+		for (int k = 0; k < N; ++k) {
+			const seq_rec nx = s_st[k + 1 < N ? k + 1 : k];  // (independent of S: in flight during the add)
+			wrong |= (unsigned)(r.e > SEQ_E_WILD && seq_binade(S) != r.e);
+			S = __dadd_rn(S, (seq_bits(S) & 1ull) ? r.d1 : r.d0);
+			r = nx;
 		}
+		if (wrong) bad = 4u;
 	}
 	if (bad) {
 		// capacity exceeded or inconsistent (never seen on CG data; tests assert the counters stay 0): the plain loop on
@@ -677,8 +714,10 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		} else {
 			S = S + ctl->tot[0];
 			ctl->n_inexact++;
+			if (st) st->seq_inexact = 1;  // the solve reports it (flof_solve.cu cg_run)
 		}
 		ctl->n_fallback++;
+		ctl->why |= bad;
 		if (bad & 4u) ctl->n_inconsistent++;
 	}
 	if (multi) {  // hand the running sum to the next rank; the last rank owns the total and tells everybody
@@ -702,6 +741,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	ctl->result = S;
 	ctl->n_dots++;
 	ctl->n_dirty += ctl->ndirty;
+	ctl->ticket = 0;
 	ctl->ndirty = 0;
 	ctl->pool_used = 0;
 	ctl->flags = 0;

@@ -207,18 +207,17 @@ __device__ __forceinline__ double dot4a(const float4 &a, const float4 &b, float 
 
 // what the reducing CG kernels need for the sequential-order dot products (pass 1, flof_seqsum.cuh)
 struct cg_seq {
-	int on;        // 1: leave per-segment prefixes for k_dot_seq and let k_seq_resolve advance the CG state
-	seq_seg *seg;
-	seq_ctl *ctl;
-	double *aggx, *agga;  // per-segment accumulators of the stencil kernel (atomics; zero between launches)
+	int on;      // 1: leave per-segment prefixes + the work list for k_dot_seq and let k_seq_resolve advance the CG state
+	seq_args A;
 };
 // tail of a reducing kernel in sequential-order mode (ONE block, every thread): per-segment prefixes, on a sharded
-// level the all-reduce that also yields the lower ranks' share; m: the block's max (thread 0), returned all-reduced
-__device__ __forceinline__ float cg_seq_tail(const cg_seq &sq, const seq_part &part, const double *px, const double *pa, float m,
-                                             bool with_max, int multi, const flof_p2p_dev &pp, double *shd, double *s_ar)
+// level the all-reduce that also yields the lower ranks' share, classification + work list of pass 2;
+// m: the block's max (thread 0), returned all-reduced
+__device__ __forceinline__ float cg_seq_tail(const cg_seq &sq, float m, bool with_max, int multi, const flof_p2p_dev &pp,
+                                             double *shd, int *shi, double *s_ar)
 {
 	double tx, ta;
-	seq_tail_scan(sq.seg, part.nseg, px, pa, shd, tx, ta);
+	seq_tail_scan(sq.A, shd, tx, ta);
 	double ox = 0., oa = 0.;
 	if (multi == 2) {
 		if (threadIdx.x == 0) {
@@ -231,44 +230,62 @@ __device__ __forceinline__ float cg_seq_tail(const cg_seq &sq, const seq_part &p
 		ox = s_ar[4];
 		oa = s_ar[5];
 	}
+	seq_tail_classify(sq.A, ox, oa, shi);
 	if (threadIdx.x == 0) {
-		sq.ctl->tot[0] = tx;
-		sq.ctl->tot[1] = ta;
-		sq.ctl->off[0] = ox;
-		sq.ctl->off[1] = oa;
+		sq.A.ctl->tot[0] = tx;
+		sq.A.ctl->tot[1] = ta;
+		sq.A.ctl->off[0] = ox;
+		sq.A.ctl->off[1] = oa;
 	}
 	return m;
 }
 
+// the streaming producers (init, update) walk `spc` consecutive segments per CTA
+struct cg_walk {
+	seq_part part;
+	int spc;
+};
+
 // res = rhs, result = 0, tmp = res*precond, srch = tmp; residual0 = max(res), sigma = tmp.res
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_cg_init(float4 *__restrict__ x, float4 *__restrict__ res, float4 *__restrict__ srch,
-              const float4 *__restrict__ grad, const float4 *__restrict__ rhs, seq_part part, float diag,
+              const float4 *__restrict__ grad, const float4 *__restrict__ rhs, cg_walk wk, float diag,
               float accuracy, int multi, cg_seq sq, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	__shared__ double shd[32];
 	__shared__ float shf[32];
+	__shared__ int shi[8];
 	__shared__ double s_ar[8];
-	double dsum = 0.;
-	float af = 0.f;
+	double csum = 0.;  // this CTA's tree partial (thread 0)
 	float mx = -3.402823466e+38f;
-	const int c0 = (int)blockIdx.x * part.seg_cells, c1 = min(c0 + part.seg_cells, part.ncells);
-	for (int c = c0 + (int)threadIdx.x; c < c1; c += FLOF_BLOCK) {
-		const float4 g = __ldg(grad + c), r = __ldg(rhs + c);
-		const float4 pc = precond_of(g, diag);
-		const float4 z = make_float4(r.x * pc.x, r.y * pc.y, r.z * pc.z, r.w * pc.w);
-		x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-		res[c] = r;
-		srch[c] = z;
-		dsum += dot4a(z, r, af);
-		mx = fmaxf(mx, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
+	const int sg1 = min(((int)blockIdx.x + 1) * wk.spc, wk.part.nseg);
+	for (int sg = (int)blockIdx.x * wk.spc; sg < sg1; ++sg) {
+		double dsum = 0.;
+		float af = 0.f;
+		const int c0 = sg * wk.part.seg_cells, c1 = min(c0 + wk.part.seg_cells, wk.part.ncells);
+		for (int c = c0 + (int)threadIdx.x; c < c1; c += FLOF_BLOCK) {
+			const float4 g = __ldg(grad + c), r = __ldg(rhs + c);
+			const float4 pc = precond_of(g, diag);
+			const float4 z = make_float4(r.x * pc.x, r.y * pc.y, r.z * pc.z, r.w * pc.w);
+			x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+			res[c] = r;
+			srch[c] = z;
+			dsum += dot4a(z, r, af);
+			mx = fmaxf(mx, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
+		}
+		double asum = (double)af;
+		seq_block_sum2(dsum, asum, shd);
+		if (threadIdx.x == 0) {
+			csum += dsum;
+			if (sq.on) {
+				sq.A.aggx[sg] = dsum;
+				sq.A.agga[sg] = asum;
+			}
+		}
 	}
-	double asum = (double)af;
-	seq_block_sum2(dsum, asum, shd);
 	mx = flof_block_max(mx, shf);
 	if (threadIdx.x == 0) {
-		red->dsum[0][blockIdx.x] = dsum;
-		red->asum[blockIdx.x] = asum;
+		red->dsum[0][blockIdx.x] = csum;
 		red->fmax[blockIdx.x] = mx;
 	}
 	if (flof_last_block(&red->counter[1])) {
@@ -282,11 +299,12 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		m = flof_block_max(m, shf);
 		if (sq.on) {
 			// sigma comes from the sequential-order dot product (k_seq_resolve finalizes the state)
-			m = cg_seq_tail(sq, part, red->dsum[0], red->asum, m, true, multi, pp, shd, s_ar);
+			m = cg_seq_tail(sq, m, true, multi, pp, shd, shi, s_ar);
 			if (threadIdx.x == 0) {
 				st->sigmaNew = s;
 				st->residual = m;
 				st->done = 0;
+				st->seq_inexact = 0;
 			}
 			return;
 		}
@@ -329,7 +347,7 @@ __global__ void k_cg_update_finalize(int maxIter, flof_cg_state *st)
 #define FLOF_APPLY_BLK 4
 #endif
 // STREAM: grad (read once) and tmp (written once) bypass the L2 residency competition with srch, which is read 9x
-template <bool STREAM, int MINB, bool SEQ>
+template <bool STREAM, int MINB, bool SEQ, int UNR>
 __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
     k_cg_apply(float4 *__restrict__ tmp, const float4 *__restrict__ srch, const float4 *__restrict__ grad,
                seq_part part, int oY, int oZ, int oT, float offd, float diag, int multi, cg_seq sq,
@@ -337,55 +355,58 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 {
 	if (st->done) return;
 	__shared__ double shd[32];
+	__shared__ int shi[8];
 	__shared__ double s_ar[8];
 	double dsum = 0.;
 	// cells < 2^29 (checked by the caller): 32-bit cell indices keep the eight neighbour addresses out of registers
-	for (int base = (int)blockIdx.x * SEQ_LEAF_CELLS + (int)threadIdx.x; base < part.ncells; base += (int)gridDim.x * SEQ_LEAF_CELLS) {
+	// c walks the four 256-cell rows of a leaf, then jumps to this CTA's next leaf (one induction variable)
+	const int gstep = ((int)gridDim.x - 1) * SEQ_LEAF_CELLS;
+	// (the outer condition is CTA-uniform -- first cell of the leaf -- so that the full-mask shuffles below are safe
+	// when the range ends inside a warp)
+	for (int c = (int)blockIdx.x * SEQ_LEAF_CELLS + (int)threadIdx.x; c - (int)threadIdx.x < part.ncells; c += gstep) {
+		const int ce = min(c - (int)threadIdx.x + SEQ_LEAF_CELLS, part.ncells);  // end of the leaf
 		double lsum = 0.;
 		float af = 0.f;
+#pragma unroll UNR
+		for (; c < ce; c += FLOF_BLOCK) {
+			const float4 g = STREAM ? __ldcs(grad + c) : __ldg(grad + c);
+			const float4 p = __ldg(srch + c);
+			float4 v;
+			if (is_border(g)) {
+				v = p;  // identity row
+			} else {
+				v = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (offd != 0.f) {
+					// neighbour order of nbx/nby/nbz/nbt (ref :389-392): t-1, z-1, y-1, x-1, x+1, y+1, z+1, t+1
+					const int o[8] = { -oT, -oZ, -oY, -1, 1, oY, oZ, oT };
 #pragma unroll
-		for (int u = 0; u < SEQ_U; ++u) {
-			const int c = base + u * FLOF_BLOCK;
-			if (c < part.ncells) {
-				const float4 g = STREAM ? __ldcs(grad + c) : __ldg(grad + c);
-				const float4 p = __ldg(srch + c);
-				float4 v;
-				if (is_border(g)) {
-					v = p;  // identity row
-				} else {
-					v = make_float4(0.f, 0.f, 0.f, 0.f);
-					if (offd != 0.f) {
-						// neighbour order of nbx/nby/nbz/nbt (ref :389-392): t-1, z-1, y-1, x-1, x+1, y+1, z+1, t+1
-						const int o[8] = { -oT, -oZ, -oY, -1, 1, oY, oZ, oT };
-#pragma unroll
-						for (int m = 0; m < 8; ++m) {
-							const float4 q = __ldg(srch + (c + o[m]));
-							v.x += offd * q.x; v.y += offd * q.y; v.z += offd * q.z; v.w += offd * q.w;
-						}
+					for (int m = 0; m < 8; ++m) {
+						const float4 q = __ldg(srch + (c + o[m]));
+						v.x += offd * q.x; v.y += offd * q.y; v.z += offd * q.z; v.w += offd * q.w;
 					}
-					// block row d: sum_m blockd(d,m) * x_m, blockd(d,m) = g_d*g_m (+ diag if d == m)  ref :483-488
-					const float gg[4] = { g.x, g.y, g.z, g.w };
-					const float pp[4] = { p.x, p.y, p.z, p.w };
-					float vv[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-					for (int dd = 0; dd < 4; ++dd) {
-#pragma unroll
-						for (int m = 0; m < 4; ++m) {
-							const float b = (dd == m) ? (gg[dd] * gg[m] + diag) : (gg[dd] * gg[m]);
-							vv[dd] += b * pp[m];
-						}
-					}
-					v = make_float4(vv[0], vv[1], vv[2], vv[3]);
 				}
-				if (STREAM)
-					__stcs(tmp + c, v);
-				else
-					tmp[c] = v;
-				if (SEQ)
-					lsum += dot4a(p, v, af);
-				else
-					dsum += dot4(p, v);
+				// block row d: sum_m blockd(d,m) * x_m, blockd(d,m) = g_d*g_m (+ diag if d == m)  ref :483-488
+				const float gg[4] = { g.x, g.y, g.z, g.w };
+				const float pp[4] = { p.x, p.y, p.z, p.w };
+				float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+				for (int dd = 0; dd < 4; ++dd) {
+#pragma unroll
+					for (int m = 0; m < 4; ++m) {
+						const float b = (dd == m) ? (gg[dd] * gg[m] + diag) : (gg[dd] * gg[m]);
+						vv[dd] += b * pp[m];
+					}
+				}
+				v = make_float4(vv[0], vv[1], vv[2], vv[3]);
 			}
+			if (STREAM)
+				__stcs(tmp + c, v);
+			else
+				tmp[c] = v;
+			if (SEQ)
+				lsum += dot4a(p, v, af);
+			else
+				dsum += dot4(p, v);
 		}
 		if (SEQ) {
 			// (every lane of the warp runs this: cells beyond the range contributed zero)
@@ -395,9 +416,9 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 				la += __shfl_down_sync(0xffffffffu, la, o);
 			}
 			if ((threadIdx.x & 31) == 0) {
-				const int sg = base / part.seg_cells;
-				atomicAdd(sq.aggx + sg, lsum);
-				atomicAdd(sq.agga + sg, la);
+				const int sg = (ce - 1) / part.seg_cells;
+				atomicAdd(sq.A.aggx + sg, lsum);
+				atomicAdd(sq.A.agga + sg, la);
 			}
 		}
 	}
@@ -407,8 +428,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 	}
 	if (flof_last_block(&red->counter[1])) {
 		if (SEQ) {  // alpha1 comes from the sequential-order dot product
-			cg_seq_tail(sq, part, sq.aggx, sq.agga, 0.f, false, multi, pp, shd, s_ar);
-			for (int b = threadIdx.x; b < part.nseg; b += blockDim.x) sq.aggx[b] = sq.agga[b] = 0.;  // for the next launch
+			cg_seq_tail(sq, 0.f, false, multi, pp, shd, shi, s_ar);
 			return;
 		}
 		double s = 0.;
@@ -423,43 +443,57 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 	}
 }
 
-// B: alpha = sigma/alpha1; result += alpha*srch; res -= alpha*tmp; partial max(res), dot(res*precond, res)
+// B: alpha = sigma/alpha1; result += alpha*srch; res -= alpha*tmp; zv = res*precond; partial max(res), dot(zv, res)
+// (zv is stored so that neither the sequential-order dot product nor the direction kernel repeats the divisions of the
+// Jacobi preconditioner: 16 B/cell written here, 16 B/cell of grad not read there)
 __global__ void __launch_bounds__(FLOF_BLOCK)
-    k_cg_update(float4 *__restrict__ x, float4 *__restrict__ res, const float4 *__restrict__ srch,
-                const float4 *__restrict__ tmp, const float4 *__restrict__ grad, seq_part part, float diag, int maxIter,
+    k_cg_update(float4 *__restrict__ x, float4 *__restrict__ res, float4 *__restrict__ zv, const float4 *__restrict__ srch,
+                const float4 *__restrict__ tmp, const float4 *__restrict__ grad, cg_walk wk, float diag, int maxIter,
                 int multi, cg_seq sq, flof_p2p_dev pp, flof_reduce_scratch *red, flof_cg_state *st)
 {
 	if (st->done) return;
 	__shared__ double shd[32];
 	__shared__ float shf[32];
+	__shared__ int shi[8];
 	__shared__ double s_ar[8];
 	const double sigma = st->sigma[st->iter & 1];
 	const double alpha = sigma / st->alpha1;  // ref :307-308
 	const double nalpha = -alpha;
-	double dsum = 0.;
-	float af = 0.f;
+	double csum = 0.;
 	float mx = -3.402823466e+38f;
-	const int c0 = (int)blockIdx.x * part.seg_cells, c1 = min(c0 + part.seg_cells, part.ncells);
-	for (int c = c0 + (int)threadIdx.x; c < c1; c += FLOF_BLOCK) {
-		const float4 p = __ldg(srch + c), ap = __ldg(tmp + c), g = __ldg(grad + c);
-		float4 xv = x[c], r = res[c];
-		xv.x = axpy1(xv.x, alpha, p.x); xv.y = axpy1(xv.y, alpha, p.y);
-		xv.z = axpy1(xv.z, alpha, p.z); xv.w = axpy1(xv.w, alpha, p.w);
-		r.x = axpy1(r.x, nalpha, ap.x); r.y = axpy1(r.y, nalpha, ap.y);
-		r.z = axpy1(r.z, nalpha, ap.z); r.w = axpy1(r.w, nalpha, ap.w);
-		x[c] = xv;
-		res[c] = r;
-		const float4 pc = precond_of(g, diag);
-		const float4 z = make_float4(r.x * pc.x, r.y * pc.y, r.z * pc.z, r.w * pc.w);
-		dsum += dot4a(z, r, af);
-		mx = fmaxf(mx, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
+	const int sg1 = min(((int)blockIdx.x + 1) * wk.spc, wk.part.nseg);
+	for (int sg = (int)blockIdx.x * wk.spc; sg < sg1; ++sg) {
+		double dsum = 0.;
+		float af = 0.f;
+		const int c0 = sg * wk.part.seg_cells, c1 = min(c0 + wk.part.seg_cells, wk.part.ncells);
+		for (int c = c0 + (int)threadIdx.x; c < c1; c += FLOF_BLOCK) {
+			const float4 p = __ldg(srch + c), ap = __ldg(tmp + c), g = __ldg(grad + c);
+			float4 xv = x[c], r = res[c];
+			xv.x = axpy1(xv.x, alpha, p.x); xv.y = axpy1(xv.y, alpha, p.y);
+			xv.z = axpy1(xv.z, alpha, p.z); xv.w = axpy1(xv.w, alpha, p.w);
+			r.x = axpy1(r.x, nalpha, ap.x); r.y = axpy1(r.y, nalpha, ap.y);
+			r.z = axpy1(r.z, nalpha, ap.z); r.w = axpy1(r.w, nalpha, ap.w);
+			x[c] = xv;
+			res[c] = r;
+			const float4 pc = precond_of(g, diag);
+			const float4 z = make_float4(r.x * pc.x, r.y * pc.y, r.z * pc.z, r.w * pc.w);
+			zv[c] = z;
+			dsum += dot4a(z, r, af);
+			mx = fmaxf(mx, fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
+		}
+		double asum = (double)af;
+		seq_block_sum2(dsum, asum, shd);
+		if (threadIdx.x == 0) {
+			csum += dsum;
+			if (sq.on) {
+				sq.A.aggx[sg] = dsum;
+				sq.A.agga[sg] = asum;
+			}
+		}
 	}
-	double asum = (double)af;
-	seq_block_sum2(dsum, asum, shd);
 	mx = flof_block_max(mx, shf);
 	if (threadIdx.x == 0) {
-		red->dsum[1][blockIdx.x] = dsum;
-		red->asum[blockIdx.x] = asum;
+		red->dsum[1][blockIdx.x] = csum;
 		red->fmax[blockIdx.x] = mx;
 	}
 	if (flof_last_block(&red->counter[2])) {
@@ -473,7 +507,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		m = flof_block_max(m, shf);
 		if (sq.on) {
 			// dot(tmp, res) comes from the sequential-order dot product, whose tail advances the state
-			m = cg_seq_tail(sq, part, red->dsum[1], red->asum, m, true, multi, pp, shd, s_ar);
+			m = cg_seq_tail(sq, m, true, multi, pp, shd, shi, s_ar);
 			if (threadIdx.x == 0) {
 				st->sigmaNew = s;
 				st->residual = m;
@@ -501,21 +535,20 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	}
 }
 
-// C: srch = res*precond + beta*srch (ref :318-323); the stop test (ref :314-317) already ran in cg_advance
+// C: srch = res*precond + beta*srch (ref :318-323) with zv = res*precond stored by B; the stop test (ref :314-317)
+// already ran in cg_advance
 __global__ void __launch_bounds__(FLOF_BLOCK)
-    k_cg_direction(float4 *__restrict__ srch, const float4 *__restrict__ res, const float4 *__restrict__ grad,
-                   int64_t cells, float diag, flof_cg_state *st)
+    k_cg_direction(float4 *__restrict__ srch, const float4 *__restrict__ zv, int64_t cells, flof_cg_state *st)
 {
 	if (st->done) return;
 	const int it = st->iter;  // iterations completed: sigma[it & 1] is the new sigma, the other slot the previous one
 	const double beta = st->sigma[it & 1] / st->sigma[(it - 1) & 1];
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
-		const float4 r = __ldg(res + c), g = __ldg(grad + c);
-		const float4 pc = precond_of(g, diag);
+		const float4 z = __ldcs(zv + c);
 		float4 p = srch[c];
-		p.x = axpy1(r.x * pc.x, beta, p.x); p.y = axpy1(r.y * pc.y, beta, p.y);
-		p.z = axpy1(r.z * pc.z, beta, p.z); p.w = axpy1(r.w * pc.w, beta, p.w);
+		p.x = axpy1(z.x, beta, p.x); p.y = axpy1(z.y, beta, p.y);
+		p.z = axpy1(z.z, beta, p.z); p.w = axpy1(z.w, beta, p.w);
 		srch[c] = p;
 	}
 }
@@ -539,6 +572,8 @@ void flof_seq_release(flof_ctx *ctx)
 	flof_seq *q = ctx->seq;
 	if (!q) return;
 	cudaFree(q->seg);
+	cudaFree(q->cls);
+	cudaFree(q->order);
 	cudaFree(q->ent);
 	cudaFree(q->ecnt);
 	cudaFree(q->aggx);
@@ -553,42 +588,46 @@ static int seq_ensure(flof_ctx *ctx)
 	flof_seq *q = (flof_seq *)calloc(1, sizeof(flof_seq));
 	if (!q) return flof_fail(ctx, FLOF_ERR_NOMEM, "flof_seq: out of host memory");
 	ctx->seq = q;
-	FLOF_CK(cudaMalloc((void **)&q->seg, sizeof(seq_seg) * FLOF_MAX_PARTIALS));
-	FLOF_CK(cudaMalloc((void **)&q->ent, sizeof(seq_rec) * (size_t)FLOF_MAX_PARTIALS * SEQ_ECAP));
-	FLOF_CK(cudaMalloc((void **)&q->ecnt, sizeof(int) * FLOF_MAX_PARTIALS));
-	FLOF_CK(cudaMalloc((void **)&q->aggx, sizeof(double) * 2 * FLOF_MAX_PARTIALS));
-	FLOF_CK(cudaMemset(q->aggx, 0, sizeof(double) * 2 * FLOF_MAX_PARTIALS));
-	q->agga = q->aggx + FLOF_MAX_PARTIALS;
+	FLOF_CK(cudaMalloc((void **)&q->seg, sizeof(seq_seg) * SEQ_MAX_SEG));
+	FLOF_CK(cudaMalloc((void **)&q->cls, sizeof(seq_cls) * SEQ_MAX_SEG));
+	FLOF_CK(cudaMalloc((void **)&q->order, sizeof(int) * SEQ_MAX_SEG));
+	FLOF_CK(cudaMalloc((void **)&q->ent, sizeof(seq_rec) * (size_t)SEQ_MAX_SEG * SEQ_ECAP));
+	FLOF_CK(cudaMalloc((void **)&q->ecnt, sizeof(int) * SEQ_MAX_SEG));
+	FLOF_CK(cudaMalloc((void **)&q->aggx, sizeof(double) * 2 * SEQ_MAX_SEG));
+	FLOF_CK(cudaMemset(q->aggx, 0, sizeof(double) * 2 * SEQ_MAX_SEG));
+	q->agga = q->aggx + SEQ_MAX_SEG;
 	FLOF_CK(cudaMalloc((void **)&q->pool, sizeof(seq_rec) * (size_t)SEQ_POOL));
 	FLOF_CK(cudaMalloc((void **)&q->ctl, sizeof(seq_ctl)));
 	FLOF_CK(cudaMemset(q->ctl, 0, sizeof(seq_ctl)));
 	FLOF_CK(cudaFuncSetAttribute(k_seq_resolve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_RESOLVE_SMEM));
 	FLOF_CK(cudaFuncSetAttribute(k_seq_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_RESOLVE_SMEM));
+	FLOF_CK(cudaFuncSetAttribute(k_dot_seq<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_DOT_SMEM));
+	FLOF_CK(cudaFuncSetAttribute(k_dot_seq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_DOT_SMEM));
 	return FLOF_OK;
 }
-static seq_args seq_make_args(flof_ctx *ctx, seq_part part, int64_t total_products)
+static seq_args seq_make_args(flof_ctx *ctx, seq_part part, int64_t products_before)
 {
 	flof_seq *q = ctx->seq;
 	seq_args A;
-	A.seg = q->seg; A.ent = q->ent; A.ecnt = q->ecnt; A.pool = q->pool; A.ctl = q->ctl;
+	A.seg = q->seg; A.cls = q->cls; A.order = q->order; A.aggx = q->aggx; A.agga = q->agga;
+	A.ent = q->ent; A.ecnt = q->ecnt; A.pool = q->pool; A.ctl = q->ctl;
 	A.part = part;
-	A.kf = seq_margin_factor(total_products);
+	A.n0 = products_before;
 	return A;
 }
 // pass 2 + resolve of one dot product whose pass 1 (per-segment prefixes in A.seg) has been enqueued
 static int seq_dot(flof_ctx *ctx, int kind, const float4 *a, const float4 *b, float diag, const seq_args &A, int mode,
                    float accuracy, int maxIter, flof_cg_state *st, int multi)
 {
-	// every CTA folds the same number of segments (+-1): one per CTA up to 4 CTAs per SM, else two, ...
+	// segments are handed out by ticket, careful ones first: one resident wave of CTAs
 	const int cap = ctx->sm_count * 4;
-	const int per = (A.part.nseg + cap - 1) / cap;
-	const int blocks = (A.part.nseg + per - 1) / per;
+	const int blocks = A.part.nseg < cap ? A.part.nseg : cap;
 	const flof_p2p_dev pp = ctx->p2p.dev;
 	if (kind == 0) {
-		FLOF_LAUNCH(k_dot_seq<0>, blocks, FLOF_BLOCK, 0, a, b, diag, A, st);
+		FLOF_LAUNCH(k_dot_seq<0>, blocks, FLOF_BLOCK, SEQ_DOT_SMEM, a, b, diag, A, st);
 		FLOF_LAUNCH(k_seq_resolve<0>, 1, FLOF_BLOCK, SEQ_RESOLVE_SMEM, a, b, diag, A, mode, accuracy, maxIter, st, multi, pp);
 	} else {
-		FLOF_LAUNCH(k_dot_seq<1>, blocks, FLOF_BLOCK, 0, a, b, diag, A, st);
+		FLOF_LAUNCH(k_dot_seq<1>, blocks, FLOF_BLOCK, SEQ_DOT_SMEM, a, b, diag, A, st);
 		FLOF_LAUNCH(k_seq_resolve<1>, 1, FLOF_BLOCK, SEQ_RESOLVE_SMEM, a, b, diag, A, mode, accuracy, maxIter, st, multi, pp);
 	}
 	return FLOF_OK;
@@ -607,6 +646,7 @@ static int seq_read_stats(flof_ctx *ctx, double *result, unsigned long long *sta
 			stats[3] = h->n_pieces; stats[4] = h->n_fallback; stats[5] = h->n_inconsistent;
 			stats[6] = h->n_slow_segments;
 			stats[7] = h->n_inexact;
+			stats[8] = h->why;
 		}
 	}
 	free(h);
@@ -614,7 +654,7 @@ static int seq_read_stats(flof_ctx *ctx, double *result, unsigned long long *sta
 	return FLOF_OK;
 }
 // test / tool entry: the sequential-order sum of a[i]*b[i] (kind 0) or (a[i]*precond(b)[i])*a[i] (kind 1) over
-// `cells` Vec4 cells.  stats (optional, 8 values): dots, dirty leaves, raw products, pieces, fallbacks, inconsistencies,
+// `cells` Vec4 cells.  stats (optional, 9 values; the last: OR of the reason flags of all fallbacks): dots, dirty leaves, raw products, pieces, fallbacks, inconsistencies,
 // careful segments, inexact (tree-sum) fallbacks since the context was created.
 extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag,
                             double *result, unsigned long long *stats)
@@ -622,7 +662,7 @@ extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64
 	FLOF_ARG(kind == 0 || kind == 1, "flof_dot_seq: kind must be 0 or 1");
 	FLOF_ARG(cells > 0 && cells < ((int64_t)1 << 29), "flof_dot_seq: cell count out of range");
 	FLOF_RET(seq_ensure(ctx));
-	const seq_args A = seq_make_args(ctx, seq_make_part(cells, 0, ctx->sm_count), 4 * cells);
+	const seq_args A = seq_make_args(ctx, seq_make_part(cells, 0, ctx->sm_count), 0);
 	if (kind == 0)
 		FLOF_LAUNCH(k_seq_agg<0>, A.part.nseg, FLOF_BLOCK, 0, (const float4 *)a, (const float4 *)b, diag, A, ctx->red);
 	else
@@ -633,12 +673,12 @@ extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64
 extern "C" int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats)
 {
 	FLOF_ARG(stats != NULL, "flof_seq_stats: stats is NULL");
-	for (int i = 0; i < 8; ++i) stats[i] = 0;
+	for (int i = 0; i < 9; ++i) stats[i] = 0;
 	if (!ctx->seq) return FLOF_OK;
 	return seq_read_stats(ctx, NULL, stats, "flof_seq_stats");
 }
 
-static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, const float *grad,
+static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, float *zvec, const float *grad,
                   const float *rhs, flof_dim4 d, float wSmooth, float wEnergy, float accuracy,
                   int maxIter, int *iters, float *relRes, int *status)
 {
@@ -660,33 +700,35 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 	// one CTA per contiguous segment of the range (reducing kernels); the direction kernel stays a flat grid-stride loop
 	const int apply_variant = ctx->opt.apply_variant;
 	const seq_part part = seq_make_part(n, sT, ctx->sm_count);
-	const int blocks = part.nseg;
+	// streaming producers: consecutive segments per CTA, about 8 CTAs per SM
+	cg_walk wk;
+	wk.part = part;
+	wk.spc = (part.nseg + ctx->sm_count * 8 - 1) / (ctx->sm_count * 8);
+	const int blocks = (part.nseg + wk.spc - 1) / wk.spc;
 	// the stencil kernel sweeps the grid leaf by leaf (grid-stride), at the occupancy of its variant
 	const int64_t nleaf = (n + SEQ_LEAF_CELLS - 1) / SEQ_LEAF_CELLS;
-	const int aper = apply_variant == 0 || apply_variant == 1 ? 4 : (apply_variant == 5 ? 6 : 8);
+	const int aper = apply_variant == 0 || apply_variant == 1 ? 4 : (apply_variant == 3 ? 5 : (apply_variant == 7 || apply_variant == 10 ? 8 : 6));
 	const int ablocks = (int)(nleaf < (int64_t)ctx->sm_count * aper ? nleaf : (int64_t)ctx->sm_count * aper);
 	const int dblocks = flof_flat_blocks(ctx, n, 8);
 	float4 *X = (float4 *)x + c0, *R = (float4 *)res + c0, *P = (float4 *)srch + c0, *AP = (float4 *)tmp + c0;
+	float4 *Z = (float4 *)zvec + c0;
 	const float4 *G = (const float4 *)grad + c0, *B = (const float4 *)rhs + c0;
 	const size_t slice_bytes = sizeof(float4) * (size_t)sT;
 	// dot products in the reference's sequential order (default): the reducing kernels leave per-segment prefixes
 	// (pass 1), k_dot_seq + k_seq_resolve deliver the exact sums and advance the state.  On a sharded level this needs
 	// the peer mailboxes (the exact running sum travels from rank to rank); the NCCL fallback keeps tree sums.
 	const int seq = (ctx->opt.dot_mode == 1 && multi != 1) ? 1 : 0;
-	cg_seq sq = { 0, NULL, NULL, NULL, NULL };
-	seq_args SA;
-	memset(&SA, 0, sizeof(SA));
+	cg_seq sq;
+	memset(&sq, 0, sizeof(sq));
 	if (seq) {
 		FLOF_RET(seq_ensure(ctx));
-		SA = seq_make_args(ctx, part, 4 * cells);
+		sq.A = seq_make_args(ctx, part, 4 * c0);  // products of the lower ranks' slabs come first in the sum
 		sq.on = 1;
-		sq.seg = ctx->seq->seg;
-		sq.ctl = ctx->seq->ctl;
-		sq.aggx = ctx->seq->aggx;
-		sq.agga = ctx->seq->agga;
 	}
-	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, X, R, P, G, B, part, k.diag, accuracy, multi, sq, pp, ctx->red, ctx->cg);
-	if (seq) FLOF_RET(seq_dot(ctx, 1, R, G, k.diag, SA, SEQ_MODE_INIT, accuracy, maxIter, ctx->cg, multi));
+	const seq_args &SA = sq.A;
+	FLOF_LAUNCH(k_cg_init, blocks, FLOF_BLOCK, 0, X, R, P, G, B, wk, k.diag, accuracy, multi, sq, pp, ctx->red, ctx->cg);
+	// (srch = res*precond after the init: the first sigma is dot(srch, res))
+	if (seq) FLOF_RET(seq_dot(ctx, 0, P, R, k.diag, SA, SEQ_MODE_INIT, accuracy, maxIter, ctx->cg, multi));
 	if (multi == 1) {
 		FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
 		FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));
@@ -703,38 +745,45 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 		if (h->done || launched >= maxIter) break;
 		for (int q = 0; q < chunk && launched < maxIter; ++q, ++launched) {
 			if (multi) FLOF_RET(flof_halo_exchange(ctx, srch, d.nt, slice_bytes, 1));
-#define FLOF_APPLY_LAUNCH(STREAM, MINB)                                                                                       \
+#define FLOF_APPLY_LAUNCH(STREAM, MINB, UNR)                                                                                  \
 	do {                                                                                                                      \
 		if (seq)                                                                                                              \
-			FLOF_LAUNCH((k_cg_apply<STREAM, MINB, true>), ablocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, part, (int)sY,    \
-			            (int)sZ, (int)sT, k.offd, k.diag, multi, sq, pp, ctx->red, ctx->cg);                                 \
+			FLOF_LAUNCH((k_cg_apply<STREAM, MINB, true, UNR>), ablocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, part,        \
+			            (int)sY, (int)sZ, (int)sT, k.offd, k.diag, multi, sq, pp, ctx->red, ctx->cg);                        \
 		else                                                                                                                  \
-			FLOF_LAUNCH((k_cg_apply<STREAM, MINB, false>), ablocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, part, (int)sY,   \
-			            (int)sZ, (int)sT, k.offd, k.diag, multi, sq, pp, ctx->red, ctx->cg);                                 \
+			FLOF_LAUNCH((k_cg_apply<STREAM, MINB, false, UNR>), ablocks, FLOF_BLOCK, 0, AP, (const float4 *)P, G, part,       \
+			            (int)sY, (int)sZ, (int)sT, k.offd, k.diag, multi, sq, pp, ctx->red, ctx->cg);                        \
 	} while (0)
 			switch (apply_variant) {
-			case 0: FLOF_APPLY_LAUNCH(false, 4); break;
-			case 1: FLOF_APPLY_LAUNCH(true, 4); break;
-			case 5: FLOF_APPLY_LAUNCH(true, 6); break;
-			default: FLOF_APPLY_LAUNCH(true, 8); break;  // 7
+			case 0: FLOF_APPLY_LAUNCH(false, 4, 4); break;
+			case 1: FLOF_APPLY_LAUNCH(true, 4, 4); break;
+			case 3: FLOF_APPLY_LAUNCH(true, 5, 4); break;
+			case 5: FLOF_APPLY_LAUNCH(true, 6, 4); break;
+			case 9: FLOF_APPLY_LAUNCH(true, 6, 2); break;
+			case 10: FLOF_APPLY_LAUNCH(true, 8, 2); break;
+			case 7: FLOF_APPLY_LAUNCH(true, 8, 1); break;
+			default: FLOF_APPLY_LAUNCH(true, 6, 1); break;  // 11: 40 registers, no spills -- measured fastest (0.184 ms at 64^4)
 			}
 			if (multi == 1) FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->alpha1, 1));
 			if (seq) FLOF_RET(seq_dot(ctx, 0, P, AP, k.diag, SA, SEQ_MODE_ALPHA, accuracy, maxIter, ctx->cg, multi));
-			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, X, R, (const float4 *)P, (const float4 *)AP, G, part, k.diag, maxIter, multi,
+			FLOF_LAUNCH(k_cg_update, blocks, FLOF_BLOCK, 0, X, R, Z, (const float4 *)P, (const float4 *)AP, G, wk, k.diag, maxIter, multi,
 			            sq, pp, ctx->red, ctx->cg);
-			if (seq) FLOF_RET(seq_dot(ctx, 1, R, G, k.diag, SA, SEQ_MODE_ADVANCE, accuracy, maxIter, ctx->cg, multi));
+			if (seq) FLOF_RET(seq_dot(ctx, 0, Z, R, k.diag, SA, SEQ_MODE_ADVANCE, accuracy, maxIter, ctx->cg, multi));
 			if (multi == 1) {
 				FLOF_RET(flof_allreduce_f64_sum(ctx, &ctx->cg->sigmaNew, 1));
 				FLOF_RET(flof_allreduce_f32_max(ctx, &ctx->cg->residual, 1));
 				FLOF_LAUNCH(k_cg_update_finalize, 1, 1, 0, maxIter, ctx->cg);
 			}
-			FLOF_LAUNCH(k_cg_direction, dblocks, FLOF_BLOCK, 0, P, (const float4 *)R, G, n, k.diag, ctx->cg);
+			FLOF_LAUNCH(k_cg_direction, dblocks, FLOF_BLOCK, 0, P, (const float4 *)Z, n, ctx->cg);
 		}
 		if (launched >= 32) chunk = 16;
 	}
 	*iters = h->iter;
 	*relRes = h->relResidual;
 	*status = h->status;
+	if (seq && h->seq_inexact)
+		return flof_fail(ctx, FLOF_ERR_ARG, "opticalFlow4d: a sequential-order dot product exceeded its capacities (sum with heavy "
+		                 "cancellation); the result would not be the reference's bits -- set dot_mode 0 for tree reductions");
 	return FLOF_OK;
 }
 
@@ -743,17 +792,20 @@ extern "C" int flof_of_cg(flof_ctx *ctx, float *x, const float *grad, const floa
                           float *relResidual)
 {
 	const size_t vb = sizeof(float) * 4 * (size_t)flof_cells(d);
-	void *res = NULL, *srch = NULL, *tmp = NULL;
-	FLOF_RET(flof_tmp_alloc(ctx, &res, vb, false));
-	FLOF_RET(flof_tmp_alloc(ctx, &srch, vb, false));
-	FLOF_RET(flof_tmp_alloc(ctx, &tmp, vb, false));
+	void *res = NULL, *srch = NULL, *tmp = NULL, *zv = NULL;
+	int rc = flof_tmp_alloc(ctx, &res, vb, false);
+	if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &srch, vb, false);
+	if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &tmp, vb, false);
+	if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &zv, vb, false);
 	int st = 0, it = 0;
 	float rr = 0.f;
-	int rc = cg_run(ctx, x, (float *)res, (float *)srch, (float *)tmp, grad, rhs, d, wSmooth, wEnergy,
-	                accuracy, maxIter, &it, &rr, &st);
+	if (rc == FLOF_OK)
+		rc = cg_run(ctx, x, (float *)res, (float *)srch, (float *)tmp, (float *)zv, grad, rhs, d, wSmooth, wEnergy,
+		            accuracy, maxIter, &it, &rr, &st);
 	flof_tmp_free(ctx, res);
 	flof_tmp_free(ctx, srch);
 	flof_tmp_free(ctx, tmp);
+	flof_tmp_free(ctx, zv);
 	if (iters) *iters = it;
 	if (relResidual) *relResidual = rr;
 	return rc;
@@ -784,19 +836,21 @@ int flof_optical_flow4d_ex(flof_ctx *ctx, float *vel, const float *i0, const flo
 	const int64_t cells = flof_cells(d);
 	FLOF_ARG(cells < ((int64_t)1 << 29), "opticalFlow4d: N = cells*4 exceeds int range (ref :376)");
 	const size_t vb = sizeof(float) * 4 * (size_t)cells;
-	void *grad = NULL, *rhs = NULL, *x = NULL, *res = NULL, *srch = NULL, *tmp = NULL;
-	FLOF_RET(flof_tmp_alloc(ctx, &grad, vb, false));
-	FLOF_RET(flof_tmp_alloc(ctx, &rhs, vb, false));
-	FLOF_RET(flof_tmp_alloc(ctx, &x, vb, false));
-	FLOF_RET(flof_tmp_alloc(ctx, &res, vb, false));
-	FLOF_RET(flof_tmp_alloc(ctx, &srch, vb, false));
-	FLOF_RET(flof_tmp_alloc(ctx, &tmp, vb, false));
-	int rc = flof_of_assemble(ctx, (float *)grad, (float *)rhs, i0, i1, vel_is_zero ? NULL : vel, d, wSmooth, wEnergy);
+	// (pool temporaries: a failed allocation releases the earlier ones below -- flof_tmp_free(NULL) is a no-op)
+	void *grad = NULL, *rhs = NULL, *x = NULL, *res = NULL, *srch = NULL, *tmp = NULL, *zv = NULL;
+	int rc = flof_tmp_alloc(ctx, &grad, vb, false);
+	if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &rhs, vb, false);
+	if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &x, vb, false);
+	if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &res, vb, false);
+	if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &srch, vb, false);
+	if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &tmp, vb, false);
+	if (rc == FLOF_OK) rc = flof_tmp_alloc(ctx, &zv, vb, false);
+	if (rc == FLOF_OK) rc = flof_of_assemble(ctx, (float *)grad, (float *)rhs, i0, i1, vel_is_zero ? NULL : vel, d, wSmooth, wEnergy);
 	int it = 0, st = 0;
 	float rr = 1e10f;
 	if (rc == FLOF_OK) {
 		cudaEventRecord(ctx->ev[2], ctx->stream);
-		rc = cg_run(ctx, (float *)x, (float *)res, (float *)srch, (float *)tmp, (const float *)grad,
+		rc = cg_run(ctx, (float *)x, (float *)res, (float *)srch, (float *)tmp, (float *)zv, (const float *)grad,
 		            (const float *)rhs, d, wSmooth, wEnergy, cgAccuracy, 1000, &it, &rr, &st);
 		cudaEventRecord(ctx->ev[3], ctx->stream);
 	}
@@ -818,6 +872,7 @@ int flof_optical_flow4d_ex(flof_ctx *ctx, float *vel, const float *i0, const flo
 	flof_tmp_free(ctx, res);
 	flof_tmp_free(ctx, srch);
 	flof_tmp_free(ctx, tmp);
+	flof_tmp_free(ctx, zv);
 	if (rc != FLOF_OK) return rc;
 	// ref :532-541 optional blur with half sigma
 	if (postVelBlur > 0.f) FLOF_RET(flof_gaussian_blur4d_impl(ctx, vel, d, 4, (float)(0.5 * postVelBlur), 1));

@@ -33,7 +33,7 @@ def test_extrapolation_kernels_agree_bit_for_bit(env):
     m = mk.download()
     assert 0.05 < float((m == 0).mean()) < 0.6           # the workload really is sparse-but-scattered
     out = {}
-    for mode in (2, 1, 0):
+    for mode in (2, 1, 0, 3):
         ctx.set_option("expol_mode", mode)
         dst.upload(start)
         ctx.cv_expol_blur4d(dst, mk, 7)
@@ -41,6 +41,7 @@ def test_extrapolation_kernels_agree_bit_for_bit(env):
     ctx.set_option("expol_mode", 1)
     assert np.array_equal(out[1], out[2])
     assert np.array_equal(out[0], out[2])
+    assert np.array_equal(out[3], out[2])                 # 4y x 2z work-list items
     # marked cells and the outer shell never change (ref knCvExpolBlur4d :613-626, bnd = 1)
     keep = (m != 0)
     keep[0], keep[-1], keep[:, 0], keep[:, -1] = True, True, True, True
@@ -57,15 +58,15 @@ def test_cg_apply_variants_same_iterations_and_bits(env):
     """The CG apply variants only change cache hints / occupancy: stopping iteration and solution bits are equal."""
     ctx, i0, i1 = env
     res = {}
-    for v in (0, 1, 7):
+    for v in (0, 1, 7, 11):
         ctx.set_option("apply_variant", v)
         vel = ctx.grid(DIMS, 4)
         it = ctx.optical_flow4d(vel, i0, i1, None, 1e-3, 1e-4, 0., 1e-2, -1.)
         res[v] = (it, vel.download())
         vel.free()
-    ctx.set_option("apply_variant", 7)
-    assert res[0][0] == res[1][0] == res[7][0]
-    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][1], res[7][1])
+    ctx.set_option("apply_variant", 11)
+    assert res[0][0] == res[1][0] == res[7][0] == res[11][0]
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][1], res[7][1]) and np.array_equal(res[0][1], res[11][1])
 
 
 def test_identical_inputs_give_zero_deformation(env):

@@ -136,7 +136,13 @@ def test_expol_work_list_paths_bitexact(gpu, dims):
     for density, sweeps in ((0.25, 3), (0.7, 2), (0.02, 4), (1.0, 1)):
         a = rnd(sh + (4,), 21, 1.3)
         mark = (rng.random(sh) >= density).astype(np.float32)   # marker != 0 -> cell keeps its value
-        eq(gpu.cv_expol_blur4d(a, mark, sweeps), port.cv_expol_blur4d(a, mark, sweeps))
+        want = port.cv_expol_blur4d(a, mark, sweeps)
+        eq(gpu.cv_expol_blur4d(a, mark, sweeps), want)
+        gpu.ctx.set_option("expol_mode", 3)                     # 4y x 2z items (odd nz, clamped planes, ragged lists)
+        try:
+            eq(gpu.cv_expol_blur4d(a, mark, sweeps), want)
+        finally:
+            gpu.ctx.set_option("expol_mode", 1)
 
 
 def test_calc_ls_diff(gpu):

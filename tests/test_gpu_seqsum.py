@@ -62,7 +62,8 @@ def test_dot_seq_bits_small(gpu, cells):
 
 
 def test_dot_seq_preconditioned_and_full_size(gpu):
-    """kind 1 (tmp = res*precond; dot(tmp, res)) with identity-row markers, at the 64^4 cell count."""
+    """kind 1 (tmp = res*precond; dot(tmp, res)) with identity-row markers and kind 0 on a CG-like pair (sum dominated by
+    one sign, like srch . A srch), at the 64^4 cell count: exact bits, carried by the parallel scheme (no fallback)."""
     rng = np.random.default_rng(9)
     cells = 64 ** 4
     res = (rng.standard_normal((cells, 4)) * 10.0 ** rng.uniform(-5, -1, (cells, 1))).astype(np.float32)
@@ -78,15 +79,32 @@ def test_dot_seq_preconditioned_and_full_size(gpu):
     assert bits(got) == bits(want), (got, want)
     got0, _ = gpu.ctx.dot_seq(da, db, 0)           # kind 0 multiplies the NaN markers in: NaN on both sides (payload free)
     assert np.isnan(got0) and np.isnan(port.dot_seq(res, grad, 0))
-    g2 = np.where(np.isnan(grad), np.float32(0.25), grad)
-    dc = gpu.ctx.to_device(g2.reshape(1, 1, 1, cells, 4))
+    # srch . A srch of an SPD system: mostly positive products, some negative ones
+    ap = (res * (1.0 + 0.5 * rng.standard_normal((cells, 4)))).astype(np.float32)
+    dc = gpu.ctx.to_device(ap.reshape(1, 1, 1, cells, 4))
     got0, _ = gpu.ctx.dot_seq(da, dc, 0)
-    assert bits(got0) == bits(port.dot_seq(res, g2, 0))
-    dc.free()
+    assert bits(got0) == bits(port.dot_seq(res, ap, 0))
     after = gpu.ctx.seq_stats()
-    assert after["fallbacks"] == before["fallbacks"], (before, after)   # the parallel scheme carried it
+    assert after["fallbacks"] == before["fallbacks"] and after["inexact"] == before["inexact"], (before, after)
     # a monotone sum crosses each binade once: only a handful of the 16384 leaves may be dirty
     assert after["dirty_leaves"] - before["dirty_leaves"] <= 400, (before, after)
+    for g in (da, db, dc):
+        g.free()
+
+
+def test_dot_seq_heavy_cancellation_falls_back_exactly(gpu):
+    """A sum that hovers around zero (random signs) is outside what the CG produces; up to 2^21 cells the resolver's
+    fallback is the plain loop -- still the exact bits -- and it is counted."""
+    rng = np.random.default_rng(11)
+    cells = 1 << 20
+    a = rng.standard_normal((cells, 4)).astype(np.float32)
+    b = rng.standard_normal((cells, 4)).astype(np.float32)
+    da = gpu.ctx.to_device(a.reshape(1, 1, 1, cells, 4))
+    db = gpu.ctx.to_device(b.reshape(1, 1, 1, cells, 4))
+    got, _ = gpu.ctx.dot_seq(da, db, 0)
+    assert bits(got) == bits(port.dot_seq(a, b, 0))
+    st = gpu.ctx.seq_stats()
+    assert st["inexact"] == 0 and st["inconsistent"] == 0, st
     da.free()
     db.free()
 
@@ -96,11 +114,12 @@ def test_solve_is_bit_identical_to_the_oracle(gpu):
     d = (24, 20, 22, 18)
     i0, i1 = sdf_pair(d, seed=5)
     v0 = np.zeros((d[3], d[2], d[1], d[0], 4), np.float32)
+    before = gpu.ctx.seq_stats()
     a, it_a = gpu.optical_flow4d(v0, i0, i1, 1e-3, 1e-4, 4., 1e-2, 0.1, want_iters=True)
     b, it_b = port.optical_flow4d(v0, i0, i1, 1e-3, 1e-4, 4., 1e-2, 0.1, want_iters=True)
     assert it_a == it_b
     assert np.array_equal(a, b), np.abs(a - b).max()
-    assert gpu.ctx.seq_stats()["fallbacks"] == 0
+    assert gpu.ctx.seq_stats()["fallbacks"] == before["fallbacks"]
 
 
 def test_mode1_small_is_bit_identical_to_the_oracle(gpu):
@@ -125,6 +144,7 @@ def test_mode1_matches_the_reference_run_bit_for_bit(gpu, name):
     from ofblend_b200 import synth
     g = np.load(os.path.join(G, name))
     dims = tuple(int(x) for x in g["dims"])
+    before = gpu.ctx.seq_stats()
     i0 = synth.post_process(synth.two_drop_phi(dims, 0), gpu)
     i1 = synth.post_process(synth.two_drop_phi(dims, 1), gpu)
     v0 = np.zeros(i0.shape + (4,), np.float32)
@@ -139,4 +159,4 @@ def test_mode1_matches_the_reference_run_bit_for_bit(gpu, name):
     assert np.array_equal(adv[sub], g["adv_sub"]), np.abs(adv[sub] - g["adv_sub"]).max() / 0.005
     assert np.allclose(errs, g["errs"], rtol=1e-6), (errs, g["errs"])
     st = gpu.ctx.seq_stats()
-    assert st["fallbacks"] == 0 and st["inconsistent"] == 0, st
+    assert st["fallbacks"] == before["fallbacks"] and st["inconsistent"] == 0 and st["inexact"] == 0, (before, st)
