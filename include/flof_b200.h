@@ -94,8 +94,9 @@ int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value);
  * which makes the whole mode-1 result bit-identical to the reference; 0 = tree reductions (last bits of the sums differ).
  * flof_dot_seq is that dot product on its own (tests, tools): kind 0 = sum a[i]*b[i], kind 1 = sum (a[i]*precond(b)[i])*a[i]
  * with the Jacobi reciprocal diagonal of grad = b (ref: precondInit/precondApply :331-354); `cells` Vec4 cells.
- * stats[9] = dot products, dirty leaves, raw products, pieces, fallbacks, failed consistency checks, segments that took
- * the careful (leaf-by-leaf) path, fallbacks that had to return the tree sum, OR of the reason flags of the fallbacks -- all since the context was created. */
+ * stats[10] = dot products, dirty leaves, raw products, pieces, fallbacks, failed consistency checks, segments that took
+ * the careful (leaf-by-leaf) path, fallbacks that had to return the tree sum, OR of the reason flags of the fallbacks,
+ * leaves kept as plain products (summed one by one) -- all since the context was created. */
 int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag, double *result,
                  unsigned long long *stats);
 int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats);

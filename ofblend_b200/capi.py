@@ -146,14 +146,14 @@ class Context:
     def dot_seq(self, a, b, kind=0, diag=0.0):
         """CG dot product in the reference's sequential summation order (flof_dot_seq); a, b: device Vec4 grids."""
         out = C.c_double(0)
-        st = (C.c_ulonglong * 9)()
+        st = (C.c_ulonglong * 10)()
         self._chk(self.lib.flof_dot_seq(self.h, a.ptr, b.ptr, C.c_int64(a.cells), int(kind), C.c_float(diag), C.byref(out), st))
         return out.value, [int(x) for x in st]
 
     def seq_stats(self):
-        st = (C.c_ulonglong * 9)()
+        st = (C.c_ulonglong * 10)()
         self._chk(self.lib.flof_seq_stats(self.h, st))
-        return dict(zip(("dots", "dirty_leaves", "raw_products", "pieces", "fallbacks", "inconsistent", "careful_segments", "inexact", "why"),
+        return dict(zip(("dots", "dirty_leaves", "raw_products", "pieces", "fallbacks", "inconsistent", "careful_segments", "inexact", "why", "raw_leaves"),
                         [int(x) for x in st]))
 
     @property

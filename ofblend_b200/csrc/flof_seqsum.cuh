@@ -25,6 +25,9 @@
 #define SEQ_DMAX 1024                        // dirty leaves the resolver can take per dot product
 #define SEQ_POOL (1 << 18)                   // pieces (32 B each) all dirty leaves of one dot product may use
 #define SEQ_STAGE 1536                       // pieces of ONE dirty leaf (k_dot_seq stages them in shared memory)
+#define SEQ_RAWLEAF_MIN 256                  // a dirty leaf that still has more pieces after merging is kept as plain products
+#define SEQ_RAWLEAF_RECS (SEQ_LEAF_CELLS * 4 * 4 / 32)  // pool records that hold the 4096 floats of such a leaf
+#define SEQ_GSTEPS (1 << 17)                 // walk steps of the resolver's global-memory list (used when SEQ_SMAX is exceeded)
 #define SEQ_EMAX 2560                        // segment entries the resolver stages in shared memory
 #define SEQ_MAX_SEG 2048                     // segments per rank
 #define SEQ_PLAIN_MAX (1 << 21)                // cells up to which the resolver's fallback is the plain one-thread loop
@@ -54,7 +57,7 @@ struct seq_ctl {  // device-resident control block of one context
 	double result;             // last resolved sum (exact bits of the sequential loop)
 	double tot[2];             // approximate sum / magnitude bound of this rank's range (tail of pass 1)
 	double off[2];             // the same for all lower ranks together (0 on a single GPU)
-	unsigned long long n_dots, n_dirty, n_raw, n_pieces, n_fallback, n_inconsistent, n_slow_segments, n_inexact;  // statistics since context creation
+	unsigned long long n_dots, n_dirty, n_raw, n_pieces, n_fallback, n_inconsistent, n_slow_segments, n_inexact, n_rawleaves;  // statistics since context creation
 };
 
 struct flof_seq {  // host-side handle (ctx->seq)
@@ -65,6 +68,7 @@ struct flof_seq {  // host-side handle (ctx->seq)
 	int *ecnt;         // [SEQ_MAX_SEG]
 	double *aggx, *agga;  // [SEQ_MAX_SEG] each: per-segment sums of pass 1 (plain stores, or atomics of the stencil kernel); zero between launches
 	seq_rec *pool;     // [SEQ_POOL]
+	seq_rec *gsteps;   // [SEQ_GSTEPS] walk steps of a dot product that does not fit the resolver's shared memory
 	seq_ctl *ctl;
 };
 

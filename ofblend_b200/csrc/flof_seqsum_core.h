@@ -35,6 +35,8 @@
 #define SEQ_E_WILD (-100000)   // leaf/piece of zeros only: identity, compatible with any binade
 #define SEQ_E_DIRTY (-100001)  // leaf record: see the dirty list
 #define SEQ_E_RAW (-100002)    // piece: one product, added with a real fp64 add
+#define SEQ_E_RAWLEAF (-100003)  // piece: a whole leaf of products kept as plain floats in the pool (pad[0] = first pool
+                                 // record of the floats, pad[1] = number of products), added one by one with real fp64 adds
 #define SEQ_E_MIN (-900)       // binades outside [MIN, MAX] (subnormal neighbourhood / overflow) are never "safe"
 #define SEQ_E_MAX (900)
 

@@ -30,6 +30,7 @@ struct seq_args {
 	seq_rec *ent;
 	int *ecnt;
 	seq_rec *pool;
+	seq_rec *gsteps;
 	seq_ctl *ctl;
 	seq_part part;
 	int64_t n0;  // products of the lower ranks' ranges (0 on a single GPU): global position of this range in the sum
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	__shared__ double shd[32];
 	__shared__ seq_fn s_fn[FLOF_BLOCK / 32];
 	__shared__ int shi[8], s_wb[8];
-	__shared__ int s_mode, s_e, s_seg;
+	__shared__ int s_mode, s_e, s_seg, s_rawbase;
 	__shared__ double s_P, s_T;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (;;) {
@@ -511,10 +512,8 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 					}
 					__syncthreads();
 					if (tid == 0) {
-						if (total > cap)
-							atomicOr(&A.ctl->flags, 2u | 0x200u);  // pieces of one dirty leaf exceed the staging area
-						else {
-							int m = 0, nraw = 0;
+						int m = 0, nraw = 0;
+						if (total <= cap) {
 							for (int w = 0; w < FLOF_BLOCK / 32; ++w) {
 								const int wb = s_wb[w], wn = shi[w];
 								for (int k = wb; k < wb + wn; ++k) {
@@ -530,20 +529,39 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 									}
 								}
 							}
-							const unsigned id = atomicAdd(&A.ctl->ndirty, 1u);
-							const unsigned base = atomicAdd(&A.ctl->pool_used, (unsigned)m);
-							if (id >= SEQ_DMAX || base + (unsigned)m > SEQ_POOL)
-								atomicOr(&A.ctl->flags, 2u | 0x400u);  // dirty-leaf list or piece pool full
-							else {
-								for (int k = 0; k < m; ++k) A.pool[base + k] = stage[k];
-								em.flush();
-								seq_rec r;
-								r.d0 = r.d1 = 0.; r.e = SEQ_E_DIRTY; r.q = 0; r.pad[0] = (int)base; r.pad[1] = m;
-								em.put(r);
-								atomicAdd(&A.ctl->n_raw, (unsigned long long)nraw);
-								atomicAdd(&A.ctl->n_pieces, (unsigned long long)m);
-							}
 						}
+						// a leaf that stays fragmented (the running sum hovers around zero or a binade boundary) is kept as
+						// its plain products: one walk step, SEQ_LEAF_CELLS * 4 real adds in the resolver
+						const bool rawleaf = total > cap || m > SEQ_RAWLEAF_MIN;
+						const unsigned need = rawleaf ? 1u + SEQ_RAWLEAF_RECS : (unsigned)m;
+						const unsigned id = atomicAdd(&A.ctl->ndirty, 1u);
+						const unsigned base = atomicAdd(&A.ctl->pool_used, need);
+						s_rawbase = -1;
+						if (id >= SEQ_DMAX || base + need > SEQ_POOL)
+							atomicOr(&A.ctl->flags, 2u | 0x400u);  // dirty-leaf list or piece pool full
+						else {
+							seq_rec r;
+							if (rawleaf) {
+								r.d0 = r.d1 = 0.; r.e = SEQ_E_RAWLEAF; r.q = 0; r.pad[0] = (int)base + 1; r.pad[1] = SEQ_LEAF_CELLS * 4;
+								A.pool[base] = r;
+								s_rawbase = (int)base + 1;
+								m = 1;
+								nraw = SEQ_LEAF_CELLS * 4;
+								atomicAdd(&A.ctl->n_rawleaves, 1ull);
+							} else
+								for (int k = 0; k < m; ++k) A.pool[base + k] = stage[k];
+							em.flush();
+							r.d0 = r.d1 = 0.; r.e = SEQ_E_DIRTY; r.q = 0; r.pad[0] = (int)base; r.pad[1] = m;
+							em.put(r);
+							atomicAdd(&A.ctl->n_raw, (unsigned long long)nraw);
+							atomicAdd(&A.ctl->n_pieces, (unsigned long long)m);
+						}
+					}
+					__syncthreads();
+					if (s_rawbase >= 0) {  // this thread's sixteen consecutive products, in order (cells beyond the range: zeros)
+						float4 *fp = reinterpret_cast<float4 *>(A.pool + s_rawbase) + tid * SEQ_U;
+#pragma unroll
+						for (int k = 0; k < SEQ_U; ++k) fp[k] = make_float4(xs[4 * k], xs[4 * k + 1], xs[4 * k + 2], xs[4 * k + 3]);
 					}
 				}
 				__syncthreads();  // s_x, s_fn and the staging area are reused by the next leaf
@@ -625,12 +643,14 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		if (tid == 0) {
 			s_D = D;
 			s_N = SEQ_CTHREADS + D + NP;
-			if (D > SEQ_DMAX || SEQ_CTHREADS + D + NP > SEQ_SMAX) atomicOr(&s_bad, 2u | 0x1000u);  // more dirty leaves / walk steps than the resolver stages
+			if (D > SEQ_DMAX || SEQ_CTHREADS + D + NP > SEQ_GSTEPS) atomicOr(&s_bad, 2u | 0x1000u);  // more dirty leaves / walk steps than the resolver takes
 		}
 	}
 	__syncthreads();
-	const bool fits = s_D <= SEQ_DMAX && s_N <= SEQ_SMAX;
+	const bool fits = s_D <= SEQ_DMAX && s_N <= SEQ_GSTEPS;
 	const int D = fits ? s_D : 0, N = fits ? s_N : 0;
+	// the walk steps live in shared memory; a dot product with more of them (rare) takes the global list: slower, same result
+	seq_rec *const steps = N <= SEQ_SMAX ? s_st : A.gsteps;
 	// ---- C: every composing thread folds the runs of its chunk into run steps, cutting at dirty leaves.
 	// First step of thread t = t + (dirty leaves before its chunk) + (their pieces): dense and ordered.
 	if (tid < SEQ_CTHREADS && fits) {
@@ -644,7 +664,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 			if (r.e == SEQ_E_DIRTY) {
 				seq_rec o;
 				o.d0 = f.d0; o.d1 = f.d1; o.e = e; o.q = f.q; o.pad[0] = o.pad[1] = 0;
-				s_st[pos++] = o;
+				steps[pos++] = o;
 				s_jsrc[dk] = r.pad[0];
 				s_jcnt[dk] = r.pad[1];
 				s_jdst[dk] = pos;
@@ -661,13 +681,13 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		}
 		seq_rec o;
 		o.d0 = f.d0; o.d1 = f.d1; o.e = e; o.q = f.q; o.pad[0] = o.pad[1] = 0;
-		s_st[pos] = o;
+		steps[pos] = o;
 		if (bad) atomicOr(&s_bad, bad);
 	}
 	__syncthreads();
 	for (int k = tid >> 5; k < D; k += FLOF_BLOCK / 32) {  // one warp per dirty leaf copies its pieces into place
 		const seq_rec *src = A.pool + s_jsrc[k];
-		seq_rec *dst = s_st + s_jdst[k];
+		seq_rec *dst = steps + s_jdst[k];
 		for (int j = tid & 31; j < s_jcnt[k]; j += 32) dst[j] = src[j];
 	}
 	__syncthreads();
@@ -689,9 +709,25 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		S = S + ctl->tot[0];
 	} else if (!bad) {
 		unsigned wrong = 0;
-		seq_rec r = s_st[0];
+		seq_rec r = steps[0];
 		for (int k = 0; k < N; ++k) {
-			const seq_rec nx = s_st[k + 1 < N ? k + 1 : k];  // (independent of S: in flight during the add)
+			const seq_rec nx = steps[k + 1 < N ? k + 1 : k];  // (independent of S: in flight during the add)
+			if (r.e == SEQ_E_RAWLEAF) {  // a leaf kept as plain products (its step record carries d0 = d1 = 0)
+				const float4 *fp = reinterpret_cast<const float4 *>(A.pool + r.pad[0]);
+				const int n4 = r.pad[1] >> 2;
+				for (int j = 0; j < n4; j += 4) {
+					float4 v[4];
+#pragma unroll
+					for (int u = 0; u < 4; ++u) v[u] = fp[j + u];
+#pragma unroll
+					for (int u = 0; u < 4; ++u) {
+						S = __dadd_rn(S, (double)v[u].x);
+						S = __dadd_rn(S, (double)v[u].y);
+						S = __dadd_rn(S, (double)v[u].z);
+						S = __dadd_rn(S, (double)v[u].w);
+					}
+				}
+			}
 			wrong |= (unsigned)(r.e > SEQ_E_WILD && seq_binade(S) != r.e);
 			S = __dadd_rn(S, (seq_bits(S) & 1ull) ? r.d1 : r.d0);
 			r = nx;

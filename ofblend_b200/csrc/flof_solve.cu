@@ -578,6 +578,7 @@ void flof_seq_release(flof_ctx *ctx)
 	cudaFree(q->ecnt);
 	cudaFree(q->aggx);
 	cudaFree(q->pool);
+	cudaFree(q->gsteps);
 	cudaFree(q->ctl);
 	free(q);
 	ctx->seq = NULL;
@@ -597,6 +598,7 @@ static int seq_ensure(flof_ctx *ctx)
 	FLOF_CK(cudaMemset(q->aggx, 0, sizeof(double) * 2 * SEQ_MAX_SEG));
 	q->agga = q->aggx + SEQ_MAX_SEG;
 	FLOF_CK(cudaMalloc((void **)&q->pool, sizeof(seq_rec) * (size_t)SEQ_POOL));
+	FLOF_CK(cudaMalloc((void **)&q->gsteps, sizeof(seq_rec) * (size_t)SEQ_GSTEPS));
 	FLOF_CK(cudaMalloc((void **)&q->ctl, sizeof(seq_ctl)));
 	FLOF_CK(cudaMemset(q->ctl, 0, sizeof(seq_ctl)));
 	FLOF_CK(cudaFuncSetAttribute(k_seq_resolve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQ_RESOLVE_SMEM));
@@ -610,7 +612,7 @@ static seq_args seq_make_args(flof_ctx *ctx, seq_part part, int64_t products_bef
 	flof_seq *q = ctx->seq;
 	seq_args A;
 	A.seg = q->seg; A.cls = q->cls; A.order = q->order; A.aggx = q->aggx; A.agga = q->agga;
-	A.ent = q->ent; A.ecnt = q->ecnt; A.pool = q->pool; A.ctl = q->ctl;
+	A.ent = q->ent; A.ecnt = q->ecnt; A.pool = q->pool; A.gsteps = q->gsteps; A.ctl = q->ctl;
 	A.part = part;
 	A.n0 = products_before;
 	return A;
@@ -647,6 +649,7 @@ static int seq_read_stats(flof_ctx *ctx, double *result, unsigned long long *sta
 			stats[6] = h->n_slow_segments;
 			stats[7] = h->n_inexact;
 			stats[8] = h->why;
+			stats[9] = h->n_rawleaves;
 		}
 	}
 	free(h);
@@ -654,7 +657,7 @@ static int seq_read_stats(flof_ctx *ctx, double *result, unsigned long long *sta
 	return FLOF_OK;
 }
 // test / tool entry: the sequential-order sum of a[i]*b[i] (kind 0) or (a[i]*precond(b)[i])*a[i] (kind 1) over
-// `cells` Vec4 cells.  stats (optional, 9 values; the last: OR of the reason flags of all fallbacks): dots, dirty leaves, raw products, pieces, fallbacks, inconsistencies,
+// `cells` Vec4 cells.  stats (optional, 10 values; [8]: OR of the reason flags of all fallbacks, [9]: leaves kept as plain products): dots, dirty leaves, raw products, pieces, fallbacks, inconsistencies,
 // careful segments, inexact (tree-sum) fallbacks since the context was created.
 extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag,
                             double *result, unsigned long long *stats)
@@ -673,7 +676,7 @@ extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64
 extern "C" int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats)
 {
 	FLOF_ARG(stats != NULL, "flof_seq_stats: stats is NULL");
-	for (int i = 0; i < 9; ++i) stats[i] = 0;
+	for (int i = 0; i < 10; ++i) stats[i] = 0;
 	if (!ctx->seq) return FLOF_OK;
 	return seq_read_stats(ctx, NULL, stats, "flof_seq_stats");
 }

@@ -160,3 +160,24 @@ def test_mode1_matches_the_reference_run_bit_for_bit(gpu, name):
     assert np.allclose(errs, g["errs"], rtol=1e-6), (errs, g["errs"])
     st = gpu.ctx.seq_stats()
     assert st["fallbacks"] == before["fallbacks"] and st["inconsistent"] == 0 and st["inexact"] == 0, (before, st)
+
+
+def test_dot_seq_fragmented_leaves_are_summed_product_by_product(gpu):
+    """A large sum (> 2^21 cells: no plain-loop fallback) whose running value hovers around zero for its first 48 leaves:
+    those leaves are kept as plain products (raw leaves) and added one by one by the resolver -- exact bits, no fallback."""
+    rng = np.random.default_rng(23)
+    cells = (1 << 22) + 4321
+    a = np.abs(rng.standard_normal((cells, 4))).astype(np.float32)
+    b = np.abs(rng.standard_normal((cells, 4))).astype(np.float32)
+    n0 = 48 * 1024
+    a[:n0] *= rng.choice(np.array([-1.0, 1.0], np.float32), size=(n0, 4))
+    da = gpu.ctx.to_device(a.reshape(1, 1, 1, cells, 4))
+    db = gpu.ctx.to_device(b.reshape(1, 1, 1, cells, 4))
+    before = gpu.ctx.seq_stats()
+    got, _ = gpu.ctx.dot_seq(da, db, 0)
+    assert bits(got) == bits(port.dot_seq(a, b, 0))
+    st = gpu.ctx.seq_stats()
+    assert st["fallbacks"] == before["fallbacks"] and st["inexact"] == 0 and st["inconsistent"] == 0, (before, st)
+    assert st["raw_leaves"] > before["raw_leaves"], (before, st)
+    da.free()
+    db.free()
