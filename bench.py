@@ -199,7 +199,9 @@ def parity_record(res, vel_h, cg_iters, errs, world):
         rec = json.load(open(N1_RECORD)).get(str(res))
     except Exception:
         rec = None
-    if rec is not None:
+    if world < 0:
+        pass  # (a run in another dot mode: not comparable with the stored record)
+    elif rec is not None:
         out["parity_vs_n1"] = bool(rec["cg_iters"] == cg_iters and rec["deformation_checksum"] == out["deformation_checksum"])
         out["n1_record"] = "tests/golden/bench_n1_record.json (single-GPU run of this bench)"
     elif world == 1:
@@ -207,7 +209,7 @@ def parity_record(res, vel_h, cg_iters, errs, world):
     return out
 
 
-def measure(ctx, api, fdist, res, steps, warmup, world, local_rank, with_e2e, prof_steps):
+def measure(ctx, api, fdist, res, steps, warmup, world, local_rank, with_e2e, prof_steps, check_n1=True):
     """Times `steps` mode-1 solves at res^4 (after `warmup`); returns a dict of everything the JSON line needs."""
     from ofblend_b200 import capi, synth
     dims = (res, res, res, res)
@@ -261,7 +263,7 @@ def measure(ctx, api, fdist, res, steps, warmup, world, local_rank, with_e2e, pr
     out["errs"] = [float(trace.errs[q]) for q in range(min(trace.n_errs, 64))]
     out["seq"] = ctx.seq_stats()
     # what the timed solve produced, checked on the host (outside every timed region)
-    out["parity"] = parity_record(res, vel.download(), out["cg_iters"], out["errs"], world)
+    out["parity"] = parity_record(res, vel.download(), out["cg_iters"], out["errs"], world if check_n1 else -1)
 
     # ---- e2e: host buffers through the plugin-level C-ABI call, copies inside the timed region
     if with_e2e:
@@ -398,6 +400,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-res128", action="store_true", help="skip the 128^4 sub-record (config.res128)")
+    ap.add_argument("--no-tree-record", action="store_true", help="skip the dot_mode 0 sub-record (config.tree_dot_mode)")
     ap.add_argument("--write-n1-record", action="store_true", help="store this run's result as the single-GPU parity record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -444,6 +447,20 @@ def main():
             m2 = None
     else:
         m2 = None
+
+    if res == 64 and not args.no_tree_record:
+        # the same solve with tree-reduced dot products (dot_mode 0, the round-1 arithmetic): faster, not the reference's bits
+        try:
+            ctx.set_option("dot_mode", 0)
+            m0 = measure(ctx, api, fdist, res, 3, 1, world, local_rank, False, 1, check_n1=False)
+            config["tree_dot_mode"] = {"note": "dot_mode 0: CG dot products as tree reductions instead of the reference's sequential order "
+                                               "(default dot_mode 1, which `value` measures); same kernels otherwise",
+                                       "value": m0["ms_per_step"] / 1e3, "unit": UNIT, "steps": 3, "warmup": 1, "cg_iters": m0["cg_iters"],
+                                       "vs_reference_run": m0["parity"].get("vs_reference_run")}
+        except Exception as e:  # noqa: BLE001
+            config["tree_dot_mode"] = {"error": str(e)[:300]}
+        finally:
+            ctx.set_option("dot_mode", 1)
 
     line = {"metric": METRIC, "value": m["ms_per_step"] / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": False,

@@ -85,18 +85,20 @@ int flof_ctx_comm_init(flof_ctx *ctx, int nranks, int rank, const char id[FLOF_C
 int flof_ctx_comm_destroy(flof_ctx *ctx);
 int flof_ctx_rank(flof_ctx *ctx);
 int flof_ctx_nranks(flof_ctx *ctx);
-/* kernel selection knobs, all bit-identical (A/B timing, tests): "expol_mode" 1 Vec4 work list (default) / 0 component
- * planes / 2 dense; "expol_variant", "apply_variant" register-budget variants (apply: 11 = default).  Defaults come from the environment
+/* kernel selection knobs, all bit-identical (A/B timing, tests): "expol_mode" 1 Vec4 work list of 4y items / 3, 4 the same with
+ * 4y x 2z, 4y x 4z items / 0 component planes / 2 dense; "expol_variant", "apply_variant" register-budget variants (apply: 11 = default).  Defaults come from the environment
  * variables FLOF_EXPOL_MODE, FLOF_EXPOL_VARIANT, FLOF_APPLY_VARIANT when the context is created. */
 int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value);
+int flof_ctx_get_option(flof_ctx *ctx, const char *name, int *value);
 /* "dot_mode": 1 (default, FLOF_DOT_MODE) = the CG's dot products are evaluated in the reference's SEQUENTIAL summation
  * order, bit for bit (ref: dotProd optflow4d.cpp:234-241 -- `for (i) d += a[i]*b[i]`, fp32 product, fp64 running sum),
  * which makes the whole mode-1 result bit-identical to the reference; 0 = tree reductions (last bits of the sums differ).
  * flof_dot_seq is that dot product on its own (tests, tools): kind 0 = sum a[i]*b[i], kind 1 = sum (a[i]*precond(b)[i])*a[i]
  * with the Jacobi reciprocal diagonal of grad = b (ref: precondInit/precondApply :331-354); `cells` Vec4 cells.
- * stats[10] = dot products, dirty leaves, raw products, pieces, fallbacks, failed consistency checks, segments that took
+ * stats[15] = dot products, dirty leaves, raw products, pieces, fallbacks, failed consistency checks, segments that took
  * the careful (leaf-by-leaf) path, fallbacks that had to return the tree sum, OR of the reason flags of the fallbacks,
- * leaves kept as plain products (summed one by one) -- all since the context was created. */
+ * leaves kept as plain products (summed one by one), then five profiling sums of the resolver (cycles of its gather /
+ * compose / walk / finish phases, walk steps) -- all since the context was created. */
 int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag, double *result,
                  unsigned long long *stats);
 int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats);

@@ -143,17 +143,23 @@ class Context:
         """Kernel selection knob (all choices bit-identical): expol_mode, expol_variant, apply_variant."""
         self._chk(self.lib.flof_ctx_set_option(self.h, name.encode(), int(value)))
 
+    def get_option(self, name):
+        v = C.c_int(0)
+        self._chk(self.lib.flof_ctx_get_option(self.h, name.encode(), C.byref(v)))
+        return int(v.value)
+
     def dot_seq(self, a, b, kind=0, diag=0.0):
         """CG dot product in the reference's sequential summation order (flof_dot_seq); a, b: device Vec4 grids."""
         out = C.c_double(0)
-        st = (C.c_ulonglong * 10)()
+        st = (C.c_ulonglong * 15)()
         self._chk(self.lib.flof_dot_seq(self.h, a.ptr, b.ptr, C.c_int64(a.cells), int(kind), C.c_float(diag), C.byref(out), st))
         return out.value, [int(x) for x in st]
 
     def seq_stats(self):
-        st = (C.c_ulonglong * 10)()
+        st = (C.c_ulonglong * 15)()
         self._chk(self.lib.flof_seq_stats(self.h, st))
-        return dict(zip(("dots", "dirty_leaves", "raw_products", "pieces", "fallbacks", "inconsistent", "careful_segments", "inexact", "why", "raw_leaves"),
+        return dict(zip(("dots", "dirty_leaves", "raw_products", "pieces", "fallbacks", "inconsistent", "careful_segments", "inexact", "why", "raw_leaves",
+                         "cyc_gather", "cyc_compose", "cyc_walk", "cyc_finish", "walk_steps"),
                         [int(x) for x in st]))
 
     @property

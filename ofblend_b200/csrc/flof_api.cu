@@ -73,7 +73,7 @@ int flof_ctx_create(flof_ctx **out, int device)
 	// break-even of a CG iteration (replicated: 41 us per Mcell; sharded over P: that / P + ~0.1 ms of halo and
 	// reduction latency) lies near 3-4 Mcells: 32^4 stays replicated, 64^4 and up are cut along t
 	c->shard_min_cells = (int64_t)1 << 22;
-	c->opt.expol_mode = getenv("FLOF_EXPOL_MODE") ? atoi(getenv("FLOF_EXPOL_MODE")) : 1;
+	c->opt.expol_mode = getenv("FLOF_EXPOL_MODE") ? atoi(getenv("FLOF_EXPOL_MODE")) : -1;  // -1: by grid size (flof_blur.cu)
 	c->opt.expol_variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
 	c->opt.apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 11;
 	c->opt.dot_mode = getenv("FLOF_DOT_MODE") ? atoi(getenv("FLOF_DOT_MODE")) : 1;
@@ -123,6 +123,17 @@ int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value)
 	else if (!strcmp(name, "dot_mode")) ctx->opt.dot_mode = value;
 	else if (!strcmp(name, "no_p2p")) ctx->opt.no_p2p = value;
 	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_set_option: unknown option '%s'", name);
+	return FLOF_OK;
+}
+int flof_ctx_get_option(flof_ctx *ctx, const char *name, int *value)
+{
+	FLOF_ARG(name != NULL && value != NULL, "flof_ctx_get_option: NULL argument");
+	if (!strcmp(name, "expol_mode")) *value = ctx->opt.expol_mode;
+	else if (!strcmp(name, "expol_variant")) *value = ctx->opt.expol_variant;
+	else if (!strcmp(name, "apply_variant")) *value = ctx->opt.apply_variant;
+	else if (!strcmp(name, "dot_mode")) *value = ctx->opt.dot_mode;
+	else if (!strcmp(name, "no_p2p")) *value = ctx->opt.no_p2p;
+	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_get_option: unknown option '%s'", name);
 	return FLOF_OK;
 }
 int flof_ctx_set_shard_min_cells(flof_ctx *ctx, int64_t cells)

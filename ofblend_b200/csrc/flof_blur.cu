@@ -165,13 +165,16 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 	if (sweeps <= 0) return FLOF_OK;
 	const size_t bytes = sizeof(float) * 4 * (size_t)flof_cells(d);
 	const size_t slice_bytes = sizeof(float) * 4 * (size_t)d.nx * d.ny * d.nz;
-	// 1 (default): Vec4 work list.  0: component planes -- bit-exact too, measured equal (0.24 vs 0.20 ms at 64^4,
-	// 4.1 vs 4.4 ms at 128^4: its scalar edge loads and pair-packing moves eat what the 4-wide x tile saves), kept
-	// selectable for further work.  2: dense kernel (no work list).
-	const int mode = ctx->opt.expol_mode;
+	// Work-list kernels, all bit-identical (tests/test_gpu_fullsize.py).  1: items of 4 y-cells; 3 / 4: items of 4y x 2z /
+	// 4y x 4z cells (27 / 20.25 row loads per output instead of 40.5; measured 3.08 / 2.94 ms per sweep at 128^4 against
+	// 4.36 ms for mode 1, 0.154 / 0.159 / 0.203 ms at 64^4); 0: component planes (4.1 ms at 128^4, plus two layout passes);
+	// 2: dense kernel (no work list).  -1 (default): 4 on large grids, 3 below.
+	int mode = ctx->opt.expol_mode;
+	if (mode < 0) mode = flof_cells(d) >= ((int64_t)1 << 25) ? 4 : 3;
 	const int64_t cap4 = mode == 0 ? flof_expol_planes_capacity(ctx, d) : 0;
-	const int64_t capz = mode == 3 ? flof_expol_z2_capacity(ctx, d) : 0;  // 3: Vec4 work list with 4y x 2z items
-	const int64_t cap1 = ((mode <= 1 || mode == 3) && cap4 == 0 && capz == 0) ? flof_expol_item_capacity(ctx, d) : 0;
+	const int tz = mode == 4 ? 4 : 2;
+	const int64_t capz = (mode == 3 || mode == 4) ? flof_expol_zn_capacity(ctx, d, tz) : 0;  // 3 / 4: Vec4 work list with 4y x 2z / 4y x 4z items
+	const int64_t cap1 = ((mode <= 1 || mode >= 3) && cap4 == 0 && capz == 0) ? flof_expol_item_capacity(ctx, d) : 0;
 	void *tmp = NULL, *tmp2 = NULL, *items = NULL, *count = NULL;
 	int rc = flof_tmp_alloc(ctx, &tmp, bytes, false);
 	int n = 0;
@@ -197,7 +200,7 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 		if (cap1 > 0 || capz > 0) {
 			// Vec4 work list: the cells that never change are copied into the second buffer once
 			if (capz > 0)
-				rc = flof_expol_z2_build(ctx, marker, d, (uint2 *)items, (unsigned int *)count, &n);
+				rc = flof_expol_zn_build(ctx, marker, d, tz, (uint2 *)items, (unsigned int *)count, &n);
 			else
 				rc = flof_expol_build(ctx, marker, d, (uint32_t *)items, (unsigned int *)count, &n);
 			if (rc == FLOF_OK) rc = flof_memcpy_d2d(ctx, oth, cur, bytes);
@@ -206,7 +209,7 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 			rc = flof_halo_exchange(ctx, cur, d.nt, slice_bytes, 1);
 			if (rc != FLOF_OK) break;
 			if (capz > 0)
-				rc = flof_launch_expol_z2(ctx, cur, oth, (const uint2 *)items, n, d);
+				rc = flof_launch_expol_zn(ctx, cur, oth, (const uint2 *)items, n, d, tz);
 			else if (cap1 > 0)
 				rc = flof_launch_expol_items(ctx, cur, oth, (const uint32_t *)items, n, d);
 			else

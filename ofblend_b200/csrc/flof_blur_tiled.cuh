@@ -362,27 +362,29 @@ static int flof_launch_expol_items(flof_ctx *ctx, const float *a, float *out, co
 	return FLOF_OK;
 }
 
-// ------------------------------------------------------------------ 81-tap extrapolation, work list, 4y x 2z items ---
-// Same work-list scheme with items of FLOF_ETPY rows x 2 z-planes: the 18 row segments of a (vt, plane) pair feed the
-// outputs of both z-planes, so an output costs 27 LDG.128 instead of 40.5 (the kernel is bound by the L1 data pipe,
-// not by its 648 packed adds per item).  Per output the taps still arrive in the reference's order (vt, zk, yj, xi):
-// planes ascend, rows ascend within a plane, and every accumulator only ever sees the planes of its own window.
+// ------------------------------------------------------------------ 81-tap extrapolation, work list, 4y x TZ z items ---
+// Same work-list scheme with items of FLOF_ETPY rows x TZ z-planes (TZ = 2 or 4): the 18 row segments of a (vt, plane)
+// pair feed the outputs of up to three z-planes, so an output costs 27 (TZ = 2) or 20.25 (TZ = 4) LDG.128 instead of
+// 40.5 -- the kernel is bound by the L1 data pipe (~2 cycles per 128-byte line), not by its 81 packed adds per output.
+// Per output the taps still arrive in the reference's order (vt, zk, yj, xi): planes ascend, rows ascend within a
+// plane, and every accumulator only ever sees the planes of its own window.
 // item = { linear id ((tl*nzb + kb)*nyb + yb)*nx + x , need-mask: bit (zo*FLOF_ETPY + oy) }
+template <int TZ>
 __global__ void __launch_bounds__(FLOF_BLOCK)
-    k_expol_build_items_z2(const float *__restrict__ mark, uint2 *__restrict__ items, unsigned int *__restrict__ count,
+    k_expol_build_items_zn(const float *__restrict__ mark, uint2 *__restrict__ items, unsigned int *__restrict__ count,
                            flof_kd d, int nyb)
 {
 	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
 	const int kb = (int)blockIdx.y, tl = (int)blockIdx.z, t = tl + d.t0;
-	const int nzb = (d.nz + 1) / 2;
+	const int nzb = (d.nz + TZ - 1) / TZ;
 	unsigned mask = 0;
 	uint32_t id = 0;
 	if (p < (unsigned)(d.nx * nyb) && t >= 1 && t < d.nt - 1) {
 		const int yb = (int)(p / (unsigned)d.nx), x = (int)(p - (unsigned)yb * (unsigned)d.nx);
 		if (x >= 1 && x < d.nx - 1) {
 #pragma unroll
-			for (int zo = 0; zo < 2; ++zo) {
-				const int k = kb * 2 + zo;
+			for (int zo = 0; zo < TZ; ++zo) {
+				const int k = kb * TZ + zo;
 				if (k < 1 || k >= d.nz - 1) continue;
 				const int64_t plane = flof_idx(d, x, 0, k, t);
 #pragma unroll
@@ -412,9 +414,9 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	if (mask) items[s_base + s_off[wid] + __popc(b & ((1u << lane) - 1u))] = make_uint2(id, mask);
 }
 
-template <int MINB>
+template <int TZ, int MINB>
 __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
-    k_cv_expol_items_z2(const float4 *__restrict__ a, float4 *__restrict__ out, const uint2 *__restrict__ items, int n,
+    k_cv_expol_items_zn(const float4 *__restrict__ a, float4 *__restrict__ out, const uint2 *__restrict__ items, int n,
                         flof_kd d, int nyb)
 {
 	const int q = (int)(blockIdx.x * FLOF_BLOCK + threadIdx.x);
@@ -422,16 +424,16 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 	const uint2 it = __ldg(items + q);
 	const unsigned mask = it.y;
 	unsigned id = it.x;
-	const int nzb = (d.nz + 1) / 2;
+	const int nzb = (d.nz + TZ - 1) / TZ;
 	const int x = (int)(id % (unsigned)d.nx);
 	id /= (unsigned)d.nx;
 	const int y0 = (int)(id % (unsigned)nyb) * FLOF_ETPY;
 	id /= (unsigned)nyb;
-	const int k0 = (int)(id % (unsigned)nzb) * 2, t = (int)(id / (unsigned)nzb) + d.t0;
+	const int k0 = (int)(id % (unsigned)nzb) * TZ, t = (int)(id / (unsigned)nzb) + d.t0;
 
-	p4 acc[2][FLOF_ETPY];
+	p4 acc[TZ][FLOF_ETPY];
 #pragma unroll
-	for (int zo = 0; zo < 2; ++zo)
+	for (int zo = 0; zo < TZ; ++zo)
 #pragma unroll
 		for (int oy = 0; oy < FLOF_ETPY; ++oy) acc[zo][oy] = p4_zero();
 	int roff[FLOF_ETPY + 2];  // offset of (x, clamp(y0-1+r)) inside a z-t plane; clamped rows only feed unneeded outputs
@@ -440,9 +442,10 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 	const int64_t sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
 #pragma unroll 1
 	for (int vt = t - 1; vt <= t + 1; ++vt) {
-#pragma unroll 1
-		for (int pz = 0; pz < 4; ++pz) {
-			// plane k0 - 1 + pz (clamped: out-of-range planes only feed outputs on the z border, which are never needed)
+		// planes k0 - 1 + pz, pz = 0 .. TZ+1 (clamped: out-of-range planes only feed outputs on the z border, which are
+		// never needed).  The plane loop is unrolled so that every accumulator is a register, not an indexed array.
+#pragma unroll
+		for (int pz = 0; pz < TZ + 2; ++pz) {
 			const float4 *base = a + (sT * vt + sZ * min(max(k0 - 1 + pz, 0), d.nz - 1));
 			p4 L[FLOF_ETPY + 2][3];
 #pragma unroll
@@ -453,8 +456,8 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 				L[r][2] = p4_load(row + 1);
 			}
 #pragma unroll
-			for (int zo = 0; zo < 2; ++zo) {
-				if (pz < zo || pz > zo + 2) continue;  // (uniform: pz is the loop counter)
+			for (int zo = 0; zo < TZ; ++zo) {
+				if (pz < zo || pz > zo + 2) continue;
 #pragma unroll
 				for (int r = 0; r < FLOF_ETPY + 2; ++r)
 #pragma unroll
@@ -469,7 +472,8 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 	}
 	const double f = 1. / 81.0;
 #pragma unroll
-	for (int zo = 0; zo < 2; ++zo) {
+	for (int zo = 0; zo < TZ; ++zo) {
+		if (!((mask >> (zo * FLOF_ETPY)) & ((1u << FLOF_ETPY) - 1u))) continue;
 		float4 *o = out + (sT * t + sZ * (k0 + zo) + (int64_t)y0 * d.nx + x);
 #pragma unroll
 		for (int oy = 0; oy < FLOF_ETPY; ++oy) {
@@ -480,39 +484,51 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 	}
 }
 
-static int64_t flof_expol_z2_capacity(const flof_ctx *ctx, flof_dim4 d)
+static int64_t flof_expol_zn_capacity(const flof_ctx *ctx, flof_dim4 d, int tz)
 {
 	int ta, tb;
 	flof_slab(ctx, d.nt, &ta, &tb);
-	const int64_t n = (int64_t)d.nx * ((d.ny + FLOF_ETPY - 1) / FLOF_ETPY) * ((d.nz + 1) / 2) * (tb - ta);
+	const int64_t n = (int64_t)d.nx * ((d.ny + FLOF_ETPY - 1) / FLOF_ETPY) * ((d.nz + tz - 1) / tz) * (tb - ta);
 	return n < ((int64_t)1 << 31) ? n : 0;
 }
-static int flof_expol_z2_build(flof_ctx *ctx, const float *marker, flof_dim4 d, uint2 *items, unsigned int *count, int *n)
+static int flof_expol_zn_build(flof_ctx *ctx, const float *marker, flof_dim4 d, int tz, uint2 *items, unsigned int *count, int *n)
 {
 	dim3 g;
 	const flof_kd kd = flof_kdim(ctx, d, &g);
 	const int nyb = (d.ny + FLOF_ETPY - 1) / FLOF_ETPY;
 	g.x = (unsigned)(((int64_t)d.nx * nyb + FLOF_BLOCK - 1) / FLOF_BLOCK);
-	g.y = (unsigned)((d.nz + 1) / 2);
+	g.y = (unsigned)((d.nz + tz - 1) / tz);
 	FLOF_CK(cudaMemsetAsync(count, 0, sizeof(unsigned int), ctx->stream));
-	FLOF_LAUNCH(k_expol_build_items_z2, g, FLOF_BLOCK, 0, marker, items, count, kd, nyb);
+	if (tz == 4)
+		FLOF_LAUNCH(k_expol_build_items_zn<4>, g, FLOF_BLOCK, 0, marker, items, count, kd, nyb);
+	else
+		FLOF_LAUNCH(k_expol_build_items_zn<2>, g, FLOF_BLOCK, 0, marker, items, count, kd, nyb);
 	unsigned int *h = (unsigned int *)ctx->pinned;
 	FLOF_CK(cudaMemcpyAsync(h, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
 	FLOF_CK(cudaStreamSynchronize(ctx->stream));
 	*n = (int)h[0];
 	return FLOF_OK;
 }
-static int flof_launch_expol_z2(flof_ctx *ctx, const float *a, float *out, const uint2 *items, int n, flof_dim4 d)
+static int flof_launch_expol_zn(flof_ctx *ctx, const float *a, float *out, const uint2 *items, int n, flof_dim4 d, int tz)
 {
 	if (n <= 0) return FLOF_OK;
 	dim3 g;
 	const flof_kd kd = flof_kdim(ctx, d, &g);
 	const int nyb = (d.ny + FLOF_ETPY - 1) / FLOF_ETPY;
 	const dim3 gi((unsigned)((n + FLOF_BLOCK - 1) / FLOF_BLOCK));
-	if (ctx->opt.expol_variant == 1)
-		FLOF_LAUNCH((k_cv_expol_items_z2<1>), gi, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)out, items, n, kd, nyb);
-	else
-		FLOF_LAUNCH((k_cv_expol_items_z2<2>), gi, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)out, items, n, kd, nyb);
+#define FLOF_EZ_LAUNCH(TZ, MINB)                                                                                      \
+	FLOF_LAUNCH((k_cv_expol_items_zn<TZ, MINB>), gi, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)out, items, n, kd, nyb)
+	if (tz == 4) {
+		if (ctx->opt.expol_variant == 1)
+			FLOF_EZ_LAUNCH(4, 1);
+		else
+			FLOF_EZ_LAUNCH(4, 2);
+	} else {
+		if (ctx->opt.expol_variant == 1)
+			FLOF_EZ_LAUNCH(2, 1);
+		else
+			FLOF_EZ_LAUNCH(2, 2);
+	}
 	return FLOF_OK;
 }
 

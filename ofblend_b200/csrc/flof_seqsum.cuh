@@ -25,7 +25,7 @@
 #define SEQ_DMAX 1024                        // dirty leaves the resolver can take per dot product
 #define SEQ_POOL (1 << 18)                   // pieces (32 B each) all dirty leaves of one dot product may use
 #define SEQ_STAGE 1536                       // pieces of ONE dirty leaf (k_dot_seq stages them in shared memory)
-#define SEQ_RAWLEAF_MIN 256                  // a dirty leaf that still has more pieces after merging is kept as plain products
+#define SEQ_RAWLEAF_MIN 1024                 // a dirty leaf that still has more pieces after merging is kept as plain products
 #define SEQ_RAWLEAF_RECS (SEQ_LEAF_CELLS * 4 * 4 / 32)  // pool records that hold the 4096 floats of such a leaf
 #define SEQ_GSTEPS (1 << 17)                 // walk steps of the resolver's global-memory list (used when SEQ_SMAX is exceeded)
 #define SEQ_EMAX 2560                        // segment entries the resolver stages in shared memory
@@ -58,13 +58,15 @@ struct seq_ctl {  // device-resident control block of one context
 	double tot[2];             // approximate sum / magnitude bound of this rank's range (tail of pass 1)
 	double off[2];             // the same for all lower ranks together (0 on a single GPU)
 	unsigned long long n_dots, n_dirty, n_raw, n_pieces, n_fallback, n_inconsistent, n_slow_segments, n_inexact, n_rawleaves;  // statistics since context creation
+	unsigned long long prof[5];  // resolver: cycles spent gathering / composing / walking / finishing, walk steps (thread 0, summed)
 };
 
 struct flof_seq {  // host-side handle (ctx->seq)
 	seq_seg *seg;      // [SEQ_MAX_SEG]
 	seq_cls *cls;      // [SEQ_MAX_SEG]
 	int *order;        // [SEQ_MAX_SEG] work list of pass 2: careful segments first (they take longest), then the safe ones
-	seq_rec *ent;      // [SEQ_MAX_SEG * SEQ_ECAP] entries of the segments, in order
+	seq_rec *ent0;     // [SEQ_MAX_SEG] first entry of every segment
+	seq_rec *ent;      // [SEQ_MAX_SEG * SEQ_ECAP] further entries of the segments, in order
 	int *ecnt;         // [SEQ_MAX_SEG]
 	double *aggx, *agga;  // [SEQ_MAX_SEG] each: per-segment sums of pass 1 (plain stores, or atomics of the stencil kernel); zero between launches
 	seq_rec *pool;     // [SEQ_POOL]

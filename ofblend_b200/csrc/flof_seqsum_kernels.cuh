@@ -27,7 +27,8 @@ struct seq_args {
 	seq_cls *cls;
 	int *order;
 	double *aggx, *agga;
-	seq_rec *ent;
+	seq_rec *ent0;  // [SEQ_MAX_SEG] first entry of every segment (dense: the resolver gathers it with coalesced loads)
+	seq_rec *ent;   // [SEQ_MAX_SEG * SEQ_ECAP] further entries of a segment (careful segments only)
 	int *ecnt;
 	seq_rec *pool;
 	seq_rec *gsteps;
@@ -312,7 +313,8 @@ struct seq_builder {  // consecutive safe products of one binade merge into one 
 
 // entry list of one segment, kept by thread 0: consecutive clean runs of one binade merge into one entry
 struct seq_emitter {
-	seq_rec *out;  // A.ent + seg * SEQ_ECAP
+	seq_rec *out0;  // A.ent0 + seg: first entry
+	seq_rec *out;   // A.ent + seg * SEQ_ECAP: the others
 	int n;
 	bool have;
 	int e;
@@ -320,8 +322,10 @@ struct seq_emitter {
 	unsigned int *flags;
 	__device__ __forceinline__ void put(const seq_rec &r)
 	{
-		if (n < SEQ_ECAP)
-			out[n] = r;
+		if (n == 0)
+			*out0 = r;
+		else if (n <= SEQ_ECAP)
+			out[n - 1] = r;
 		else
 			atomicOr(flags, 2u | 0x100u);   // segment entry list full
 		++n;
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		const int seg = A.order[s_seg];
 		const int c0 = seg * A.part.seg_cells, c1 = min(c0 + A.part.seg_cells, A.part.ncells);
 		seq_emitter em;
-		em.out = A.ent + (size_t)seg * SEQ_ECAP; em.n = 0; em.have = false; em.e = 0; em.f = seq_identity();
+		em.out0 = A.ent0 + seg; em.out = A.ent + (size_t)seg * SEQ_ECAP; em.n = 0; em.have = false; em.e = 0; em.f = seq_identity();
 		em.flags = &A.ctl->flags;
 		double P = 0., T = 0.;  // running approximate prefix (thread 0)
 		if (tid == 0) {
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		}
 		if (tid == 0) {
 			em.flush();
-			A.ecnt[seg] = em.n < SEQ_ECAP ? em.n : SEQ_ECAP;
+			A.ecnt[seg] = em.n <= SEQ_ECAP ? em.n : SEQ_ECAP + 1;
 		}
 		__syncthreads();  // s_mode / s_fn are rewritten for the next segment
 	}
@@ -580,7 +584,42 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 // dynamic shared memory of the resolver: all segment entries, then the flat list of walk steps
 #define SEQ_CTHREADS 64  // threads that compose entry chunks (one run step each + their dirty leaves)
 #define SEQ_SMAX 4096    // walk steps (run steps + pieces of the dirty leaves) staged in shared memory
-#define SEQ_RESOLVE_SMEM ((size_t)(SEQ_EMAX + SEQ_SMAX) * sizeof(seq_rec) + (size_t)SEQ_DMAX * 3 * sizeof(int))
+#define SEQ_RAWMAX 64    // leaves kept as plain products the walk takes per dot product
+#define SEQ_RESOLVE_SMEM ((size_t)(SEQ_EMAX + SEQ_SMAX) * sizeof(seq_rec) + (size_t)SEQ_DMAX * 4 * sizeof(int))
+
+// A walk step is a seq_rec whose e / q fields are re-used: S <- S + (mantissa of S odd ? d1 : d0), and a run step also
+// checks that S lies in the binade the run was built for: ((hi32(S) >> 20) ^ e) & q must be 0 with e = biased exponent,
+// q = 0x7ff (q = 0 for raw products, identities and the place holders of raw leaves: no check, d0 = d1).
+#define SEQ_STEP(r)                                                                         \
+	{                                                                                       \
+		const int hi_ = __double2hiint(S), lo_ = __double2loint(S);                         \
+		wrong |= (unsigned)(((hi_ >> 20) ^ (r).e) & (int)(r).q);                            \
+		S = __dadd_rn(S, (lo_ & 1) ? (r).d1 : (r).d0);                                      \
+	}
+// the sequential part: one thread, ~10 instructions per step, the records of eight steps in flight
+__device__ __forceinline__ void seq_walk(const seq_rec *st, int k0, int k1, double &S, unsigned &wrong)
+{
+	int k = k0;
+	for (; k + 8 <= k1; k += 8) {
+		seq_rec r[8];
+#pragma unroll
+		for (int u = 0; u < 8; ++u) r[u] = st[k + u];
+#pragma unroll
+		for (int u = 0; u < 8; ++u) SEQ_STEP(r[u]);
+	}
+	for (; k < k1; ++k) {
+		const seq_rec r = st[k];
+		SEQ_STEP(r);
+	}
+}
+__device__ __forceinline__ seq_rec seq_run_step(const seq_fn &f, int e)
+{
+	seq_rec o;
+	o.d0 = f.d0; o.d1 = f.d1; o.pad[0] = o.pad[1] = 0;
+	o.e = e > SEQ_E_WILD ? e + 1023 : 0;
+	o.q = e > SEQ_E_WILD ? 0x7ffu : 0u;
+	return o;
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(FLOF_BLOCK)
@@ -593,41 +632,82 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	seq_rec *s_st = s_in + SEQ_EMAX;                             // [SEQ_SMAX] walk steps, in order
 	int *s_jsrc = reinterpret_cast<int *>(s_st + SEQ_SMAX);      // [SEQ_DMAX] copy jobs of the dirty leaves: pool offset,
 	int *s_jcnt = s_jsrc + SEQ_DMAX;                             //            piece count,
-	int *s_jdst = s_jcnt + SEQ_DMAX;                             //            first step
+	int *s_jdst = s_jcnt + SEQ_DMAX;                             //            first step,
+	int *s_jpfx = s_jdst + SEQ_DMAX;                             //            pieces of all earlier leaves
 	__shared__ int shi[8];
 	__shared__ unsigned s_bad;
-	__shared__ int s_E, s_D, s_N;
+	__shared__ int s_E, s_D, s_N, s_NP, s_nraw, s_nx;
+	__shared__ int s_rawpos[SEQ_RAWMAX], s_rawsrc[SEQ_RAWMAX], s_rawcnt[SEQ_RAWMAX];
 	const int tid = threadIdx.x;
 	seq_ctl *ctl = A.ctl;
+	long long tp[5];  // phase time stamps of thread 0 (seq_ctl::prof)
+	tp[0] = clock64();
 	const unsigned flags = ctl->flags;
 	const int nseg = A.part.nseg;
-	if (tid == 0) s_bad = (flags & ~1u) | (ctl->ndirty > SEQ_DMAX ? 2u | 0x400u : 0u);
-	// ---- A: gather the segment entries in order
+	if (tid == 0) {
+		s_bad = (flags & ~1u) | (ctl->ndirty > SEQ_DMAX ? 2u | 0x400u : 0u);
+		s_nraw = 0;
+		s_nx = 0;
+	}
+	__syncthreads();
+	// ---- A: gather the segment entries in order.  The first entry of every segment comes from the dense array (all
+	// loads of a thread in flight at once); only careful segments have more.
 	{
-		const int per = (nseg + FLOF_BLOCK - 1) / FLOF_BLOCK;
+		const int per = (nseg + FLOF_BLOCK - 1) / FLOF_BLOCK;  // <= 8 (SEQ_MAX_SEG / FLOF_BLOCK)
 		const int b0 = min(tid * per, nseg), b1 = min(b0 + per, nseg);
-		int cnt[8], sum = 0;  // per <= 8 (SEQ_MAX_SEG / FLOF_BLOCK)
+		int cnt[8], sum = 0;
+		seq_rec first[8];
 #pragma unroll
-		for (int q = 0; q < 8; ++q) {
-			cnt[q] = b0 + q < b1 ? A.ecnt[b0 + q] : 0;
-			sum += cnt[q];
-		}
+		for (int q = 0; q < 8; ++q) cnt[q] = b0 + q < b1 ? __ldcg(A.ecnt + b0 + q) : 0;
+#pragma unroll
+		for (int q = 0; q < 8; ++q)
+			if (b0 + q < b1) {
+				const double2 lo = __ldcg(reinterpret_cast<const double2 *>(A.ent0 + b0 + q));
+				const int4 hi = __ldcg(reinterpret_cast<const int4 *>(A.ent0 + b0 + q) + 1);
+				first[q].d0 = lo.x; first[q].d1 = lo.y; first[q].e = hi.x; first[q].q = (unsigned)hi.y;
+				first[q].pad[0] = hi.z; first[q].pad[1] = hi.w;
+			}
+#pragma unroll
+		for (int q = 0; q < 8; ++q) sum += cnt[q];
 		int total;
 		int off = seq_block_exscan_int(sum, shi, total);
 		if (tid == 0) s_E = total;
 		if (total <= SEQ_EMAX) {
 #pragma unroll
 			for (int q = 0; q < 8; ++q) {
-				for (int k = 0; k < cnt[q]; ++k) s_in[off + k] = A.ent[(size_t)(b0 + q) * SEQ_ECAP + k];
+				if (cnt[q] > 0) s_in[off] = first[q];
+				if (cnt[q] > 1) {
+					// further entries (careful segments; they cluster, one thread would fetch dozens one after the other):
+					// left as a copy job for the whole CTA (the job arrays of the dirty leaves are still free here)
+					const int jb = atomicAdd(&s_nx, 1);
+					if (jb < SEQ_DMAX) {
+						s_jsrc[jb] = b0 + q;
+						s_jdst[jb] = off + 1;
+						s_jcnt[jb] = cnt[q] - 1;
+					} else
+						for (int k = 1; k < cnt[q]; ++k) s_in[off + k] = A.ent[(size_t)(b0 + q) * SEQ_ECAP + k - 1];
+				}
 				off += cnt[q];
 			}
 		} else if (tid == 0)
 			atomicOr(&s_bad, 2u | 0x800u);  // more segment entries than the resolver stages
 	}
 	__syncthreads();
+	{  // the copy jobs: eight lanes per job, 32 jobs of the CTA in flight at once
+		const int J = min(s_nx, SEQ_DMAX);
+		for (int jb = tid >> 3; jb < J; jb += FLOF_BLOCK / 8) {
+			const seq_rec *src = A.ent + (size_t)s_jsrc[jb] * SEQ_ECAP;
+			seq_rec *dst = s_in + s_jdst[jb];
+			const int c = s_jcnt[jb];
+			for (int k = tid & 7; k < c; k += 8) dst[k] = src[k];
+		}
+	}
+	__syncthreads();
+	tp[1] = clock64();
 	const int E = s_E <= SEQ_EMAX ? s_E : 0;
 	// ---- B: SEQ_CTHREADS threads own consecutive chunks of entries: dirty leaves and pieces per chunk -> step offsets
-	const int chunk = (E + SEQ_CTHREADS - 1) / SEQ_CTHREADS;
+	// (an odd chunk length keeps the 32-byte records of neighbouring threads out of the same shared-memory banks)
+	const int chunk = ((E + SEQ_CTHREADS - 1) / SEQ_CTHREADS) | 1;
 	const int e0 = tid < SEQ_CTHREADS ? min(tid * chunk, E) : E, e1 = tid < SEQ_CTHREADS ? min(e0 + chunk, E) : E;
 	int dbefore, pbefore;
 	{
@@ -642,19 +722,21 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		pbefore = seq_block_exscan_int(np, shi, NP);
 		if (tid == 0) {
 			s_D = D;
+			s_NP = NP;
 			s_N = SEQ_CTHREADS + D + NP;
 			if (D > SEQ_DMAX || SEQ_CTHREADS + D + NP > SEQ_GSTEPS) atomicOr(&s_bad, 2u | 0x1000u);  // more dirty leaves / walk steps than the resolver takes
 		}
 	}
 	__syncthreads();
 	const bool fits = s_D <= SEQ_DMAX && s_N <= SEQ_GSTEPS;
-	const int D = fits ? s_D : 0, N = fits ? s_N : 0;
+	const int D = fits ? s_D : 0, N = fits ? s_N : 0, NP = fits ? s_NP : 0;
 	// the walk steps live in shared memory; a dot product with more of them (rare) takes the global list: slower, same result
-	seq_rec *const steps = N <= SEQ_SMAX ? s_st : A.gsteps;
+	const bool in_smem = N <= SEQ_SMAX;
+	seq_rec *const steps = in_smem ? s_st : A.gsteps;
 	// ---- C: every composing thread folds the runs of its chunk into run steps, cutting at dirty leaves.
 	// First step of thread t = t + (dirty leaves before its chunk) + (their pieces): dense and ordered.
 	if (tid < SEQ_CTHREADS && fits) {
-		int pos = tid + dbefore + pbefore, dk = dbefore;
+		int pos = tid + dbefore + pbefore, dk = dbefore, pk = pbefore;
 		seq_fn f = seq_identity();
 		int e = SEQ_E_WILD;
 		unsigned bad = 0;
@@ -662,13 +744,13 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 			const seq_rec r = s_in[k];
 			if (r.e == SEQ_E_WILD) continue;
 			if (r.e == SEQ_E_DIRTY) {
-				seq_rec o;
-				o.d0 = f.d0; o.d1 = f.d1; o.e = e; o.q = f.q; o.pad[0] = o.pad[1] = 0;
-				steps[pos++] = o;
+				steps[pos++] = seq_run_step(f, e);
 				s_jsrc[dk] = r.pad[0];
 				s_jcnt[dk] = r.pad[1];
 				s_jdst[dk] = pos;
+				s_jpfx[dk] = pk;
 				pos += r.pad[1];
+				pk += r.pad[1];
 				++dk;
 				f = seq_identity();
 				e = SEQ_E_WILD;
@@ -679,21 +761,40 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 			const seq_fn g = { r.d0, r.d1, r.q };
 			f = seq_compose(f, g);
 		}
-		seq_rec o;
-		o.d0 = f.d0; o.d1 = f.d1; o.e = e; o.q = f.q; o.pad[0] = o.pad[1] = 0;
-		steps[pos] = o;
+		steps[pos] = seq_run_step(f, e);
 		if (bad) atomicOr(&s_bad, bad);
 	}
 	__syncthreads();
-	for (int k = tid >> 5; k < D; k += FLOF_BLOCK / 32) {  // one warp per dirty leaf copies its pieces into place
-		const seq_rec *src = A.pool + s_jsrc[k];
-		seq_rec *dst = steps + s_jdst[k];
-		for (int j = tid & 31; j < s_jcnt[k]; j += 32) dst[j] = src[j];
+	// the pieces of all dirty leaves, flat over the CTA: piece -> its leaf by bisection of the piece prefixes
+	for (int p = tid; p < NP; p += FLOF_BLOCK) {
+		int lo = 0, hi = D - 1;
+		while (lo < hi) {
+			const int mid = (lo + hi + 1) >> 1;
+			if (s_jpfx[mid] <= p)
+				lo = mid;
+			else
+				hi = mid - 1;
+		}
+		const int j = p - s_jpfx[lo];
+		seq_rec r = A.pool[s_jsrc[lo] + j];
+		if (r.e == SEQ_E_RAWLEAF) {
+			const int i = atomicAdd(&s_nraw, 1);
+			if (i < SEQ_RAWMAX) {
+				s_rawpos[i] = s_jdst[lo] + j;
+				s_rawsrc[i] = r.pad[0];
+				s_rawcnt[i] = r.pad[1];
+			} else
+				atomicOr(&s_bad, 2u | 0x2000u);  // more raw leaves than the walk's side list takes
+			r.d0 = r.d1 = 0.;
+		}
+		r.q = r.e > SEQ_E_WILD ? 0x7ffu : 0u;  // (raw products carry d0 = d1 = the product)
+		r.e = r.e > SEQ_E_WILD ? r.e + 1023 : 0;
+		steps[s_jdst[lo] + j] = r;
 	}
 	__syncthreads();
 	if (tid != 0) return;
-	// ---- D: the sequential walk (one thread).  A step adds d0 / d1 by the parity of the running sum's mantissa; raw
-	// products carry d0 = d1 = the product, identity steps zeros -- one select + one fp64 add per step on the critical path
+	tp[2] = clock64();
+	// ---- D: the sequential walk (one thread)
 	double S = 0.;
 	unsigned int cseq = 0;
 	if (multi) {  // the running sum continues from the rank below (exact bits handed over through the mailboxes)
@@ -709,28 +810,47 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		S = S + ctl->tot[0];
 	} else if (!bad) {
 		unsigned wrong = 0;
-		seq_rec r = steps[0];
-		for (int k = 0; k < N; ++k) {
-			const seq_rec nx = steps[k + 1 < N ? k + 1 : k];  // (independent of S: in flight during the add)
-			if (r.e == SEQ_E_RAWLEAF) {  // a leaf kept as plain products (its step record carries d0 = d1 = 0)
-				const float4 *fp = reinterpret_cast<const float4 *>(A.pool + r.pad[0]);
-				const int n4 = r.pad[1] >> 2;
-				for (int j = 0; j < n4; j += 4) {
-					float4 v[4];
-#pragma unroll
-					for (int u = 0; u < 4; ++u) v[u] = fp[j + u];
-#pragma unroll
-					for (int u = 0; u < 4; ++u) {
-						S = __dadd_rn(S, (double)v[u].x);
-						S = __dadd_rn(S, (double)v[u].y);
-						S = __dadd_rn(S, (double)v[u].z);
-						S = __dadd_rn(S, (double)v[u].w);
-					}
-				}
+		const int nraw = s_nraw;
+		for (int i = 1; i < nraw; ++i) {  // raw leaves in walk order (a handful at most)
+			const int p = s_rawpos[i], sr = s_rawsrc[i], c = s_rawcnt[i];
+			int j = i - 1;
+			for (; j >= 0 && s_rawpos[j] > p; --j) {
+				s_rawpos[j + 1] = s_rawpos[j];
+				s_rawsrc[j + 1] = s_rawsrc[j];
+				s_rawcnt[j + 1] = s_rawcnt[j];
 			}
-			wrong |= (unsigned)(r.e > SEQ_E_WILD && seq_binade(S) != r.e);
-			S = __dadd_rn(S, (seq_bits(S) & 1ull) ? r.d1 : r.d0);
-			r = nx;
+			s_rawpos[j + 1] = p; s_rawsrc[j + 1] = sr; s_rawcnt[j + 1] = c;
+		}
+		int k = 0;
+		for (int i = 0; i <= nraw; ++i) {
+			const int kend = i < nraw ? s_rawpos[i] : N;
+			if (in_smem)
+				seq_walk(s_st, k, kend, S, wrong);
+			else
+				seq_walk(A.gsteps, k, kend, S, wrong);
+			if (i == nraw) break;
+			// a leaf kept as plain products: sixteen float4 per batch, the next batch in flight while this one is added
+			const float4 *fp = reinterpret_cast<const float4 *>(A.pool + s_rawsrc[i]);
+			const int n4 = s_rawcnt[i] >> 2;
+			float4 cur[16], nxv[16];
+#pragma unroll
+			for (int u = 0; u < 16; ++u) cur[u] = __ldcg(fp + u);
+			for (int j = 0; j < n4; j += 16) {
+				if (j + 16 < n4) {
+#pragma unroll
+					for (int u = 0; u < 16; ++u) nxv[u] = __ldcg(fp + j + 16 + u);
+				}
+#pragma unroll
+				for (int u = 0; u < 16; ++u) {
+					S = __dadd_rn(S, (double)cur[u].x);
+					S = __dadd_rn(S, (double)cur[u].y);
+					S = __dadd_rn(S, (double)cur[u].z);
+					S = __dadd_rn(S, (double)cur[u].w);
+				}
+#pragma unroll
+				for (int u = 0; u < 16; ++u) cur[u] = nxv[u];
+			}
+			k = kend + 1;  // (the place holder step of the raw leaf adds nothing)
 		}
 		if (wrong) bad = 4u;
 	}
@@ -756,6 +876,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		ctl->why |= bad;
 		if (bad & 4u) ctl->n_inconsistent++;
 	}
+	tp[3] = clock64();
 	if (multi) {  // hand the running sum to the next rank; the last rank owns the total and tells everybody
 		if (pp.rank < pp.nranks - 1) {
 			flof_mbox_hdr *nx = (flof_mbox_hdr *)pp.peer[pp.rank + 1];
@@ -789,4 +910,10 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		else if (mode == SEQ_MODE_INIT)
 			cg_init_finalize(st, S, st->residual, accuracy);
 	}
+	tp[4] = clock64();
+	ctl->prof[0] += (unsigned long long)(tp[1] - tp[0]);  // gather of the segment entries
+	ctl->prof[1] += (unsigned long long)(tp[2] - tp[1]);  // compose + piece copies
+	ctl->prof[2] += (unsigned long long)(tp[3] - tp[2]);  // walk (on a sharded level including the wait for the rank below)
+	ctl->prof[3] += (unsigned long long)(tp[4] - tp[3]);  // rank chain + state update
+	ctl->prof[4] += (unsigned long long)N;                // walk steps
 }

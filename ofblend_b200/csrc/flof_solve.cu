@@ -574,6 +574,7 @@ void flof_seq_release(flof_ctx *ctx)
 	cudaFree(q->seg);
 	cudaFree(q->cls);
 	cudaFree(q->order);
+	cudaFree(q->ent0);
 	cudaFree(q->ent);
 	cudaFree(q->ecnt);
 	cudaFree(q->aggx);
@@ -592,6 +593,7 @@ static int seq_ensure(flof_ctx *ctx)
 	FLOF_CK(cudaMalloc((void **)&q->seg, sizeof(seq_seg) * SEQ_MAX_SEG));
 	FLOF_CK(cudaMalloc((void **)&q->cls, sizeof(seq_cls) * SEQ_MAX_SEG));
 	FLOF_CK(cudaMalloc((void **)&q->order, sizeof(int) * SEQ_MAX_SEG));
+	FLOF_CK(cudaMalloc((void **)&q->ent0, sizeof(seq_rec) * (size_t)SEQ_MAX_SEG));
 	FLOF_CK(cudaMalloc((void **)&q->ent, sizeof(seq_rec) * (size_t)SEQ_MAX_SEG * SEQ_ECAP));
 	FLOF_CK(cudaMalloc((void **)&q->ecnt, sizeof(int) * SEQ_MAX_SEG));
 	FLOF_CK(cudaMalloc((void **)&q->aggx, sizeof(double) * 2 * SEQ_MAX_SEG));
@@ -612,7 +614,7 @@ static seq_args seq_make_args(flof_ctx *ctx, seq_part part, int64_t products_bef
 	flof_seq *q = ctx->seq;
 	seq_args A;
 	A.seg = q->seg; A.cls = q->cls; A.order = q->order; A.aggx = q->aggx; A.agga = q->agga;
-	A.ent = q->ent; A.ecnt = q->ecnt; A.pool = q->pool; A.gsteps = q->gsteps; A.ctl = q->ctl;
+	A.ent0 = q->ent0; A.ent = q->ent; A.ecnt = q->ecnt; A.pool = q->pool; A.gsteps = q->gsteps; A.ctl = q->ctl;
 	A.part = part;
 	A.n0 = products_before;
 	return A;
@@ -650,6 +652,7 @@ static int seq_read_stats(flof_ctx *ctx, double *result, unsigned long long *sta
 			stats[7] = h->n_inexact;
 			stats[8] = h->why;
 			stats[9] = h->n_rawleaves;
+			for (int i = 0; i < 5; ++i) stats[10 + i] = h->prof[i];
 		}
 	}
 	free(h);
@@ -657,7 +660,7 @@ static int seq_read_stats(flof_ctx *ctx, double *result, unsigned long long *sta
 	return FLOF_OK;
 }
 // test / tool entry: the sequential-order sum of a[i]*b[i] (kind 0) or (a[i]*precond(b)[i])*a[i] (kind 1) over
-// `cells` Vec4 cells.  stats (optional, 10 values; [8]: OR of the reason flags of all fallbacks, [9]: leaves kept as plain products): dots, dirty leaves, raw products, pieces, fallbacks, inconsistencies,
+// `cells` Vec4 cells.  stats (optional, 15 values; [10..14]: resolver cycles gather / compose / walk / finish and walk steps; [8]: OR of the reason flags of all fallbacks, [9]: leaves kept as plain products): dots, dirty leaves, raw products, pieces, fallbacks, inconsistencies,
 // careful segments, inexact (tree-sum) fallbacks since the context was created.
 extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64_t cells, int kind, float diag,
                             double *result, unsigned long long *stats)
@@ -676,7 +679,7 @@ extern "C" int flof_dot_seq(flof_ctx *ctx, const float *a, const float *b, int64
 extern "C" int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats)
 {
 	FLOF_ARG(stats != NULL, "flof_seq_stats: stats is NULL");
-	for (int i = 0; i < 10; ++i) stats[i] = 0;
+	for (int i = 0; i < 15; ++i) stats[i] = 0;
 	if (!ctx->seq) return FLOF_OK;
 	return seq_read_stats(ctx, NULL, stats, "flof_seq_stats");
 }

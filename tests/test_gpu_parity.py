@@ -138,11 +138,13 @@ def test_expol_work_list_paths_bitexact(gpu, dims):
         mark = (rng.random(sh) >= density).astype(np.float32)   # marker != 0 -> cell keeps its value
         want = port.cv_expol_blur4d(a, mark, sweeps)
         eq(gpu.cv_expol_blur4d(a, mark, sweeps), want)
-        gpu.ctx.set_option("expol_mode", 3)                     # 4y x 2z items (odd nz, clamped planes, ragged lists)
+        default_mode = gpu.ctx.get_option("expol_mode")
         try:
-            eq(gpu.cv_expol_blur4d(a, mark, sweeps), want)
+            for mode in (1, 3, 4):                              # 4y / 4y x 2z / 4y x 4z items (odd nz, clamped planes, ragged lists)
+                gpu.ctx.set_option("expol_mode", mode)
+                eq(gpu.cv_expol_blur4d(a, mark, sweeps), want)
         finally:
-            gpu.ctx.set_option("expol_mode", 1)
+            gpu.ctx.set_option("expol_mode", default_mode)
 
 
 def test_calc_ls_diff(gpu):

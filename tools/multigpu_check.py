@@ -40,11 +40,15 @@ def main():
         out[proj] = dict(iters_single=it_a, iters_sharded=it_b, rel_l2=rel_l2(b, a), maxabs=float(np.abs(a - b).max()),
                          errs_single=err_a, errs_sharded=err_b)
     dist.barrier(ctx)
+    # sequential-order dot products (default) over the peer mailboxes: the sharded solve must deliver the single-GPU bits;
+    # with the NCCL fallback (FLOF_NO_P2P=1: tree sums, all-reduce order) only the conditioning band can be asserted
+    exact = ctx.get_option("dot_mode") == 1 and not os.environ.get("FLOF_NO_P2P")
+    tol = (0.0, 0.0) if exact else (1e-6, 1e-2)
     ok = (out[False]["iters_single"] == out[False]["iters_sharded"] and out[True]["iters_single"] == out[True]["iters_sharded"]
-          and out[False]["rel_l2"] <= 1e-6 and out[True]["rel_l2"] <= 1e-2
+          and out[False]["rel_l2"] <= tol[0] and out[True]["rel_l2"] <= tol[1]
           and np.allclose(out[False]["errs_single"], out[False]["errs_sharded"], rtol=1e-4))
     if rank == 0:
-        print(json.dumps({"world": world, "dims": dims, "ok": bool(ok), "no_projection": out[False], "with_projection": out[True]}))
+        print(json.dumps({"world": world, "dims": dims, "ok": bool(ok), "bit_identical_required": bool(exact), "seq_dot_stats": ctx.seq_stats(), "no_projection": out[False], "with_projection": out[True]}))
     ctx.close()
     return 0 if ok else 1
 

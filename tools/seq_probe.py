@@ -24,4 +24,7 @@ n = max(st["dots"], 1)
 print(st)
 print("per dot: dirty leaves %.1f  raw %.1f  pieces %.1f  careful segments %.1f" % (
     st["dirty_leaves"] / n, st["raw_products"] / n, st["pieces"] / n, st["careful_segments"] / n))
+clk = 1.965e3  # cycles per microsecond at the B200's 1965 MHz
+print("resolver per dot: gather %.1f us  compose %.1f us  walk %.1f us (%.0f steps)  finish %.1f us" % (
+    st["cyc_gather"] / n / clk, st["cyc_compose"] / n / clk, st["cyc_walk"] / n / clk, st["walk_steps"] / n, st["cyc_finish"] / n / clk))
 ctx.close()
