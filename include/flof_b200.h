@@ -287,6 +287,32 @@ int flof_load_advect_time_slice(flof_ctx *ctx, const float *defo_vec4, flof_dim4
                                 const float defoScale[4], const float defoFactor[4],
                                 const float overrideSize[4], float overrideTimeOff, int bordSkip,
                                 float defoAniFac);
+/* ---- deformation volumes (flof.py `thirdload`: two / three deformations composed per output frame) -----------------
+ * The reference keeps, per deformation file, a window of Tw = int(dimT * max(0.2, partialLoadFac)) time slices around the
+ * current source time (LoadAdvectData::updateDefoVol :1822-1863).  Here the whole volume is resident on the device and the
+ * window is refreshed from it by the same rule (lastT == t: nothing; lastT + 1 == t: shift by one slice and fetch the
+ * last; else refetch all; slice index clamp(t - Tw/2 + tl, 0, dimT-1)).  win: wd.nt slices of wd.nx*ny*nz Vec4.
+ * vt: the one-slice scratch grid the slices pass through (the same grid flof_defovol_compose writes, like lats.tmp);
+ * *filepos: position of the reference's re-used gz handle of this file (-1 before its first use, fileio.cpp:903-919). */
+int flof_defovol_window_update(flof_ctx *ctx, float *win_vec4, flof_dim4 wd, const float *vol_vec4, int dimT, int t,
+                               int lastT, float *vt_vec4, int *filepos);
+/* vt (ONE slice, Vec4) from the windows: 2 volumes (dvol3 NULL; doAligned 0 :2019-2033, 1 :2035-2060 -- needs the
+ * window-sized scratch dvt) or 3 volumes (:2063-2081).  tcoord = srcTime - (t - Tw/2).  The caller then runs
+ * flof_lookup_slice4d_with_vel on vt with dt = 1 (ref :2086-2104). */
+int flof_defovol_compose(flof_ctx *ctx, float *vt_vec4, const float *dvol1, const float *dvol2, const float *dvol3,
+                         float *dvt_scratch, flof_dim4 wd, float tcoord, int doAligned, float blendAlpha, float thirdAlpha,
+                         float fourthAlpha);
+/* the source-time arithmetic of loadAdvectTimeSlice[_OptRun] (ref :1962-1985): host only, no device work */
+int flof_lats_source_time(flof_dim4 dd, flof_dim4 d, float time, float loadTimeScale, const float defoOffset[4],
+                          const float defoScale[4], const float overrideSize[4], float *srcTime, int *t, int *tp1,
+                          float *tw, float srcFac3[3], float off3[3]);
+/* the unoptimised loadAdvectTimeSlice (ref :1671-1760): look-up of every interior cell (bnd 1) of dst3 with dt =
+ * blendAlpha, plus its optional debug outputs debugVel (Vec3, 3 floats per cell) / debugVelT (either may be NULL) */
+int flof_load_advect_time_slice_unopt(flof_ctx *ctx, const float *defo_vec4, flof_dim4 dd, float *dst3, flof_dim3 d3,
+                                      const float *phi, flof_dim4 d, float time, float blendAlpha, float loadTimeScale,
+                                      const float defoOffset[4], const float defoScale[4], const float defoFactor[4],
+                                      const float overrideSize[4], float overrideTimeOff, float defoAniFac, int zeroVel,
+                                      float *dbgVel3, float *dbgVelT);
 /* ref: simpleBlurSpecial test.cpp:127 */
 int flof_simple_blur_special(flof_ctx *ctx, float *a, flof_dim3 d, int iter, float thresh,
                              int bord);

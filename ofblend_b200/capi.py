@@ -552,6 +552,74 @@ class HostAPI:
             return p.download()
         return self._run([phi], f)
 
+    def load_advect_defovols(self, vols, d3, phi, times, blendAlpha, thirdAlpha, fourthAlpha, loadTimeScale, defoOffset,
+                             defoScale, defoFactor, doAligned=False, partialLoadFac=0.2, overrideSize=-1., overrideTimeOff=0.,
+                             bordSkip=1, defoAniFac=1.):
+        """n frames through 2 / 3 deformation volumes, orchestrated like the `manta` module's _OptInit(useDefoVols=True) /
+        _OptAdd / _OptRun: window refresh, composition of the one-slice field, look-up (ref optflow4d.cpp:1822-1863,
+        1951-2105)."""
+        ctx = self.ctx
+        lib = ctx.lib
+
+        def f(p, *dv):
+            dd = dv[0].d4()
+            dimT = int(dd.nt)
+            Tw = int(np.float32(dimT) * max(np.float32(0.2), np.float32(partialLoadFac)))
+            wdims = (int(dd.nx), int(dd.ny), int(dd.nz), Tw)
+            wins = [ctx.grid(wdims, 4) for _ in dv]
+            for w in wins:
+                ctx._chk(lib.flof_grid_set_const(ctx.h, w.ptr, C.c_int64(w.cells), 4, _f4(0.)))
+            dvt = ctx.grid(wdims, 4) if doAligned else None
+            vt = ctx.grid(wdims[:3] + (1,), 4)
+            out = ctx.grid((d3[0], d3[1], d3[2], 1), 1)
+            frames = []
+            lastT = -1
+            filepos = [C.c_int(-1) for _ in dv]
+            ctx._chk(lib.flof_grid_set_const(ctx.h, vt.ptr, C.c_int64(vt.cells), 4, _f4(0.)))
+            fac = _f4(np.asarray(np.broadcast_to(np.asarray(defoFactor, np.float32), (4,))) * np.float32(defoAniFac))
+            for time in times:
+                srcTime, t = C.c_float(0), C.c_int(0)
+                sf3, off3 = (C.c_float * 3)(), (C.c_float * 3)()
+                lib.flof_lats_source_time(dd, p.d4(), C.c_float(time), C.c_float(loadTimeScale), _f4(defoOffset), _f4(defoScale),
+                                          _f4(overrideSize), C.byref(srcTime), C.byref(t), None, None, sf3, off3)
+                for w, v, fp in zip(wins, dv, filepos):
+                    ctx._chk(lib.flof_defovol_window_update(ctx.h, w.ptr, Dim4(*wdims), v.ptr, dimT, t.value, lastT, vt.ptr, C.byref(fp)))
+                lastT = t.value
+                tcoord = np.float32(srcTime.value) - np.float32(t.value - Tw // 2)
+                ctx._chk(lib.flof_defovol_compose(ctx.h, vt.ptr, wins[0].ptr, wins[1].ptr, wins[2].ptr if len(wins) > 2 else None,
+                                                  dvt.ptr if dvt else None, Dim4(*wdims), C.c_float(tcoord), int(bool(doAligned)),
+                                                  C.c_float(blendAlpha), C.c_float(thirdAlpha), C.c_float(fourthAlpha)))
+                ctx._chk(lib.flof_grid_set_const(ctx.h, out.ptr, C.c_int64(out.cells), 1, _f4(0.)))
+                ctx._chk(lib.flof_lookup_slice4d_with_vel(
+                    ctx.h, out.ptr, Dim3(*[int(x) for x in d3]), p.ptr, p.d4(), C.c_float(np.float32(time) + np.float32(overrideTimeOff)),
+                    C.c_float(1.0), vt.ptr, Dim3(*wdims[:3]), sf3, off3, fac, int(bordSkip)))
+                frames.append(out.download().reshape(d3[2], d3[1], d3[0]))
+            for g in wins + [vt, out] + ([dvt] if dvt else []):
+                g.free()
+            return np.stack(frames)
+        return self._run([phi] + list(vols), f)
+
+    def load_advect_time_slice_unopt(self, defo, d3, phi, time, blendAlpha, loadTimeScale, defoOffset, defoScale, defoFactor,
+                                     overrideSize=-1., overrideTimeOff=0., defoAniFac=1., zeroVel=False):
+        """The unoptimised loadAdvectTimeSlice: returns (dst, debugVel, debugVelT)."""
+        ctx = self.ctx
+
+        def f(dv, p):
+            out = ctx.grid((d3[0], d3[1], d3[2], 1), 1)
+            dbg3 = ctx.grid((d3[0] * 3, d3[1], d3[2], 1), 1)     # Vec3 grid: 3 floats per cell
+            dbgt = ctx.grid((d3[0], d3[1], d3[2], 1), 1)
+            ctx._chk(ctx.lib.flof_grid_set_const(ctx.h, out.ptr, C.c_int64(out.cells), 1, _f4(0.)))
+            ctx._chk(ctx.lib.flof_load_advect_time_slice_unopt(
+                ctx.h, dv.ptr, dv.d4(), out.ptr, Dim3(*[int(x) for x in d3]), p.ptr, p.d4(), C.c_float(time),
+                C.c_float(blendAlpha), C.c_float(loadTimeScale), _f4(defoOffset), _f4(defoScale), _f4(defoFactor),
+                _f4(overrideSize), C.c_float(overrideTimeOff), C.c_float(defoAniFac), int(bool(zeroVel)), dbg3.ptr, dbgt.ptr))
+            res = (out.download().reshape(d3[2], d3[1], d3[0]), dbg3.download().reshape(d3[2], d3[1], d3[0], 3),
+                   dbgt.download().reshape(d3[2], d3[1], d3[0]))
+            for g in (out, dbg3, dbgt):
+                g.free()
+            return res
+        return self._run([defo, phi], f)
+
     def load_advect_time_slice(self, defo, d3, phi, time, blendAlpha, loadTimeScale, defoOffset, defoScale,
                                defoFactor, overrideSize=-1., overrideTimeOff=0., bordSkip=1, defoAniFac=1., dst=None):
         ctx = self.ctx

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 
 static int lookup_launch(flof_ctx *ctx, float *dst3, flof_dim3 d3, const float *phi, flof_dim4 d, float time,
                          float dt, const float *v1, const float *v2, float f1, float f2, flof_dim3 vd,
-                         const float srcFac3[3], const float off3[3], const float fac[4], int bordSkip)
+                         const float srcFac3[3], const float off3[3], const float fac[4], int bordSkip, int kernelBnd = 10)
 {
 	FLOF_ARG(vd.nx >= 2 && vd.ny >= 2, "loadAdvectTimeSlice: Invalid src size");
 	FLOF_ARG(d.nx >= 2 && d.ny >= 2 && d.nz >= 2 && d.nt >= 2, "loadAdvectTimeSlice: phi grid too small");
@@ -232,7 +232,7 @@ static int lookup_launch(flof_ctx *ctx, float *dst3, flof_dim3 d3, const float *
 	vs.v2 = (const float4 *)v2;
 	vs.f1 = f1;
 	vs.f2 = f2;
-	const int bord = bordSkip > 10 ? bordSkip : 10;  // KERNEL(bnd = 10) and the bordSkip test (ref :1648, 1656)
+	const int bord = bordSkip > kernelBnd ? bordSkip : kernelBnd;  // KERNEL(bnd = 10) and the bordSkip test (ref :1648, 1656)
 	FLOF_LAUNCH(k_lookup_slice4d, flof_grid3(d3), FLOF_BLOCK, 0, dst3, d3, phi, d, time, dt, vs, vd,
 	            make_float3(srcFac3[0], srcFac3[1], srcFac3[2]), make_float3(off3[0], off3[1], off3[2]),
 	            make_float4(fac[0], fac[1], fac[2], fac[3]), bord);
@@ -282,6 +282,208 @@ extern "C" int flof_load_advect_time_slice(flof_ctx *ctx, const float *defo, flo
 	const flof_dim3 vd = { dd.nx, dd.ny, dd.nz };
 	return lookup_launch(ctx, dst3, d3, phi, d, time + overrideTimeOff, blendAlpha, defo + nv * 4 * t,
 	                     defo + nv * 4 * tp1, f1, f2, vd, sourceFactor, off2, fac, bordSkip);
+}
+
+// ------------------------------------------------------------------ deformation volumes ----
+// ref: LoadAdvectData::updateDefoVol :1822-1863 and the defo-volume branches of loadAdvectTimeSlice_OptRun :2015-2089
+// (flof.py `thirdload`: two or three deformations composed on the fly).  Every deformation volume stays resident on the
+// device; the reference's window of Tw = int(dimT * max(0.2, partialLoadFac)) time slices around the current source
+// time is materialised from it with the reference's own update rule -- including its start-up quirk: the very first
+// request at t = 0 takes the "one slice further" branch (lastT + 1 == t) and fills only the last window slice.
+
+// the three cases of updateDefoVol for one volume; win: Tw slices of nv cells, vol: dimT slices.
+// Slices travel through the one-slice scratch grid vt like in the reference (lats.tmp, which is also the output of the
+// composition), and the "one slice further" branch reads through the reference's re-used gz handle: the FIRST such read
+// opens the file and seeks to the requested slice, every later one just takes the next slice of the file whatever index
+// is asked for, and past the end of the file nothing is read, so that vt keeps its content (readGrid4dUni, fileio.cpp:
+// 903-919).  *filepos: next slice of that handle, -1 = not open yet.  Identical to plain indexing whenever the caller
+// advances one source slice at a time, which is what flof.py does.
+extern "C" int flof_defovol_window_update(flof_ctx *ctx, float *win, flof_dim4 wd, const float *vol, int dimT, int t,
+                                          int lastT, float *vt, int *filepos)
+{
+	FLOF_ARG(wd.nt >= 1 && dimT >= 1, "defo volume: empty window");
+	FLOF_ARG(vt != NULL && filepos != NULL, "defo volume: scratch slice / file position missing");
+	const int Tw = wd.nt, currt = Tw / 2;
+	const size_t sb = sizeof(float) * 4 * (size_t)wd.nx * wd.ny * wd.nz;
+	char *w = (char *)win;
+	const char *v = (const char *)vol;
+	if (lastT == t) return FLOF_OK;
+	if (lastT + 1 == t) {
+		// shift all back by one slice (ascending: every slice takes its successor's content), then read the last one
+		for (int tl = 0; tl < Tw - 1; ++tl)
+			FLOF_CK(cudaMemcpyAsync(w + sb * tl, w + sb * (tl + 1), sb, cudaMemcpyDeviceToDevice, ctx->stream));
+		const int tl = Tw - 1;
+		int it = min(max(t - currt + tl, 0), dimT - 1);
+		if (*filepos >= 0) it = *filepos;  // re-used handle: sequential read
+		if (it < dimT) FLOF_CK(cudaMemcpyAsync(vt, v + sb * it, sb, cudaMemcpyDeviceToDevice, ctx->stream));
+		*filepos = it < dimT ? it + 1 : it;
+		FLOF_CK(cudaMemcpyAsync(w + sb * tl, vt, sb, cudaMemcpyDeviceToDevice, ctx->stream));
+		return FLOF_OK;
+	}
+	for (int tl = 0; tl < Tw; ++tl) {
+		const int it = min(max(t - currt + tl, 0), dimT - 1);
+		FLOF_CK(cudaMemcpyAsync(w + sb * tl, v + sb * it, sb, cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	// (the reference read these through vt as well: it ends up holding the last slice)
+	FLOF_CK(cudaMemcpyAsync(vt, w + sb * (Tw - 1), sb, cudaMemcpyDeviceToDevice, ctx->stream));
+	return FLOF_OK;
+}
+
+__device__ __forceinline__ float4 f4_scale(float s, const float4 &v) { return make_float4(s * v.x, s * v.y, s * v.z, s * v.w); }
+__device__ __forceinline__ float4 f4_add(const float4 &a, const float4 &b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// MODE 0: two volumes, "aligned w/o backmove" :2019-2033      vt = bA * dvol1(q - v2) + tA * v2,  v2 = dvol2(q)
+// MODE 1: three volumes :2063-2081                            vt = bA * v1 + tA * v2 + fA * v3 (each looked up behind the later ones)
+// MODE 2: second stage of "align & move back" :2052-2060      vt = dvt(q - (1 - bA) * (-dvol1(q)))
+// MODE 3: first stage of the same :2043-2051 over the WHOLE window grid (t = slice index): dvt = bA * dvol1(q - v2) + tA * v2
+template <int MODE>
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_defovol_compose(float4 *__restrict__ out, const float4 *__restrict__ dv1, const float4 *__restrict__ dv2,
+                      const float4 *__restrict__ dv3, flof_dim4 wd, float tcoord, float bA, float tA, float fA)
+{
+	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
+	if (p >= (unsigned)(wd.nx * wd.ny)) return;
+	const int j = p / wd.nx, i = p - j * wd.nx, k = blockIdx.y, tl = blockIdx.z;
+	const float tc = MODE == 3 ? (float)tl : tcoord;
+	const float qx = (float)i + 0.5f, qy = (float)j + 0.5f, qz = (float)k + 0.5f, qt = tc + 0.5f;
+	float4 r;
+	if (MODE == 0 || MODE == 3) {
+		const float4 v2 = flof_interpol4d<float4>(dv2, wd, qx, qy, qz, qt);
+		const float4 a = flof_interpol4d<float4>(dv1, wd, qx - v2.x, qy - v2.y, qz - v2.z, qt - v2.w);
+		r = f4_add(f4_scale(bA, a), f4_scale(tA, v2));
+	} else if (MODE == 1) {
+		const float4 v3 = flof_interpol4d<float4>(dv3, wd, qx, qy, qz, qt);
+		const float rx = qx - v3.x, ry = qy - v3.y, rz = qz - v3.z, rt = qt - v3.w;
+		const float4 v2 = flof_interpol4d<float4>(dv2, wd, rx, ry, rz, rt);
+		const float4 v1 = flof_interpol4d<float4>(dv1, wd, rx - v2.x, ry - v2.y, rz - v2.z, rt - v2.w);
+		r = f4_add(f4_add(f4_scale(bA, v1), f4_scale(tA, v2)), f4_scale(fA, v3));
+	} else {
+		// dv2 = dvt here.  v1 = dvol1(q) * -1; offset (1. - blendAlpha) * v1: a double scalar times a float vector,
+		// rounded to float per component (Vector4D operator*(S2, Vector4D<S>), util/vector4d.h:244-248)
+		const float4 a = flof_interpol4d<float4>(dv1, wd, qx, qy, qz, qt);
+		const double w = 1. - (double)bA;
+		const float sx = (float)(w * (double)(a.x * -1.f)), sy = (float)(w * (double)(a.y * -1.f));
+		const float sz = (float)(w * (double)(a.z * -1.f)), st = (float)(w * (double)(a.w * -1.f));
+		r = flof_interpol4d<float4>(dv2, wd, qx - sx, qy - sy, qz - sz, qt - st);
+	}
+	out[(int64_t)i + (int64_t)wd.nx * (j + (int64_t)wd.ny * (k + (int64_t)wd.nz * tl))] = r;
+}
+
+// vt (one slice, nx*ny*nz Vec4) from the windows of 2 or 3 deformation volumes.  dvt: scratch of the window's size, only
+// used (and required) with doAligned.  tcoord = srcTime - defovolOff.
+extern "C" int flof_defovol_compose(flof_ctx *ctx, float *vt, const float *dvol1, const float *dvol2, const float *dvol3,
+                                    float *dvt, flof_dim4 wd, float tcoord, int doAligned, float blendAlpha, float thirdAlpha,
+                                    float fourthAlpha)
+{
+	FLOF_ARG(wd.nx >= 2 && wd.ny >= 2 && wd.nz >= 2 && wd.nt >= 2, "defo volumes: window too small");
+	FLOF_ARG(dvol1 && dvol2, "Code currently only supports 2 deformation volumes");  // ref :2083
+	const dim3 g1((unsigned)((wd.nx * wd.ny + FLOF_BLOCK - 1) / FLOF_BLOCK), (unsigned)wd.nz, 1);
+	const float4 *d1 = (const float4 *)dvol1, *d2 = (const float4 *)dvol2, *d3 = (const float4 *)dvol3;
+	if (dvol3) {
+		FLOF_LAUNCH(k_defovol_compose<1>, g1, FLOF_BLOCK, 0, (float4 *)vt, d1, d2, d3, wd, tcoord, blendAlpha, thirdAlpha, fourthAlpha);
+	} else if (!doAligned) {
+		FLOF_LAUNCH(k_defovol_compose<0>, g1, FLOF_BLOCK, 0, (float4 *)vt, d1, d2, d3, wd, tcoord, blendAlpha, thirdAlpha, fourthAlpha);
+	} else {
+		FLOF_ARG(dvt != NULL, "defo volumes: the aligned composition needs the window-sized scratch grid");
+		const dim3 gw(g1.x, (unsigned)wd.nz, (unsigned)wd.nt);
+		FLOF_LAUNCH(k_defovol_compose<3>, gw, FLOF_BLOCK, 0, (float4 *)dvt, d1, d2, d3, wd, 0.f, blendAlpha, thirdAlpha, fourthAlpha);
+		FLOF_LAUNCH(k_defovol_compose<2>, g1, FLOF_BLOCK, 0, (float4 *)vt, d1, (const float4 *)dvt, d3, wd, tcoord, blendAlpha, thirdAlpha, fourthAlpha);
+	}
+	return FLOF_OK;
+}
+
+// the source-time arithmetic of loadAdvectTimeSlice[_OptRun] (ref :1962-1985) for callers that manage the deformation
+// slices / windows themselves: srcTime, the two slice indices, the blend weight and the 3D look-up transform
+extern "C" int flof_lats_source_time(flof_dim4 dd, flof_dim4 d, float time, float loadTimeScale, const float defoOffset[4],
+                                     const float defoScale[4], const float overrideSize[4], float *srcTimeOut, int *tOut,
+                                     int *tp1Out, float *twOut, float srcFac3[3], float off3[3])
+{
+	const int dimT = dd.nt;
+	const float dim4[4] = { (float)dd.nx, (float)dd.ny, (float)dd.nz, (float)dimT };
+	float defoSize[4] = { (float)d.nx, (float)d.ny, (float)d.nz, (float)d.nt };
+	if (overrideSize[0] > 0.f)
+		for (int c = 0; c < 4; ++c) defoSize[c] = (float)(int)overrideSize[c];
+	const float m1[4] = { -1.f, -1.f, -1.f, -1.f };
+	float sourceFactor[4], off2[4] = { defoOffset[0], defoOffset[1], defoOffset[2], defoOffset[3] };
+	flof_grid_factor4d(dim4, defoSize, m1, defoScale, sourceFactor, off2);
+	const volatile float a = time * sourceFactor[3];
+	const volatile float b = a * loadTimeScale;
+	const volatile float c2 = b + off2[3];
+	const float srcTime = (float)((double)c2 - 0.5);
+	int t = (int)srcTime;
+	int tp1 = t + 1;
+	const float tw = srcTime - (float)t;
+	t = t < dimT - 1 ? t : dimT - 1;
+	tp1 = tp1 < dimT - 1 ? tp1 : dimT - 1;
+	if (srcTimeOut) *srcTimeOut = srcTime;
+	if (tOut) *tOut = t;
+	if (tp1Out) *tp1Out = tp1;
+	if (twOut) *twOut = tw;
+	for (int c = 0; c < 3; ++c) {
+		if (srcFac3) srcFac3[c] = sourceFactor[c];
+		if (off3) off3[c] = off2[c];
+	}
+	return 0;
+}
+
+// debug outputs of the unoptimised loadAdvectTimeSlice (ref :1731-1753): the time-blended deformation slice
+// re-interpolated to the output size and scaled, split into a Vec3 grid (3 floats per cell) and a Real grid.
+// Interior cells only (FOR_IJK_BND(vdst, 1) over a cleared grid): the outer shell is zero.
+__global__ void __launch_bounds__(FLOF_BLOCK)
+    k_slice_vel_debug(float *__restrict__ dbgVel3, float *__restrict__ dbgVelT, flof_dim3 d3, blend_slice vs, flof_dim3 vd,
+                      float3 fac3, float3 off3, float4 fac)
+{
+	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
+	if (p >= (unsigned)(d3.nx * d3.ny)) return;
+	const int j = p / d3.nx, i = p - j * d3.nx, k = blockIdx.y;
+	float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (i >= 1 && j >= 1 && k >= 1 && i < d3.nx - 1 && j < d3.ny - 1 && k < d3.nz - 1) {
+		const float x = (float)i * fac3.x + off3.x, y = (float)j * fac3.y + off3.y, z = (float)k * fac3.z + off3.z;
+		v = interp3_blend(vs, vd, x, y, z);
+		v.x *= fac.x; v.y *= fac.y; v.z *= fac.z; v.w *= fac.w;
+	}
+	const int64_t c = (int64_t)i + (int64_t)d3.nx * (j + (int64_t)d3.ny * k);
+	if (dbgVel3) {
+		dbgVel3[3 * c] = v.x;
+		dbgVel3[3 * c + 1] = v.y;
+		dbgVel3[3 * c + 2] = v.z;
+	}
+	if (dbgVelT) dbgVelT[c] = v.w;
+}
+// The unoptimised loadAdvectTimeSlice (ref :1671-1760): v1 *= (1 - tw); v2 *= tw; v1 += v2; the slice is re-interpolated
+// to the output size for the interior cells (vdst, outer shell zero), scaled by defoFactor * defoAniFac, optionally
+// returned as debugVel / debugVelT, and knSemiLagrangeLookupSlice4d (KERNEL(fourd, bnd = 1) on a one-slice grid: the
+// generated code runs it as a 3D kernel with t = 0) looks every interior cell of dst up in phi with dt = blendAlpha.
+// Same arithmetic as the optimised path with a border of 1 instead of max(10, bordSkip).
+extern "C" int flof_load_advect_time_slice_unopt(flof_ctx *ctx, const float *defo, flof_dim4 dd, float *dst3, flof_dim3 d3,
+                                                 const float *phi, flof_dim4 d, float time, float blendAlpha,
+                                                 float loadTimeScale, const float defoOffset[4], const float defoScale[4],
+                                                 const float defoFactor[4], const float overrideSize[4],
+                                                 float overrideTimeOff, float defoAniFac, int zeroVel, float *dbgVel3,
+                                                 float *dbgVelT)
+{
+	float srcTime, tw, sf3[3], off3[3];
+	int t, tp1;
+	flof_lats_source_time(dd, d, time, loadTimeScale, defoOffset, defoScale, overrideSize, &srcTime, &t, &tp1, &tw, sf3, off3);
+	FLOF_ARG(t >= 0, "loadAdvectTimeSlice: source time %g before the deformation volume", (double)srcTime);
+	FLOF_ARG(dd.nx >= 2 && dd.ny >= 2, "loadAdvectTimeSlice: Invalid src size");
+	const int64_t nv = (int64_t)dd.nx * dd.ny * dd.nz;
+	const float f1 = zeroVel ? 0.f : (float)(1. - (double)tw), f2 = zeroVel ? 0.f : tw;
+	float fac[4];
+	for (int c = 0; c < 4; ++c) fac[c] = defoFactor[c] * defoAniFac;
+	const flof_dim3 vd = { dd.nx, dd.ny, dd.nz };
+	if (dbgVel3 || dbgVelT) {
+		blend_slice vs;
+		vs.v1 = (const float4 *)(defo + nv * 4 * t);
+		vs.v2 = (const float4 *)(defo + nv * 4 * tp1);
+		vs.f1 = f1;
+		vs.f2 = f2;
+		FLOF_LAUNCH(k_slice_vel_debug, flof_grid3(d3), FLOF_BLOCK, 0, dbgVel3, dbgVelT, d3, vs, vd,
+		            make_float3(sf3[0], sf3[1], sf3[2]), make_float3(off3[0], off3[1], off3[2]),
+		            make_float4(fac[0], fac[1], fac[2], fac[3]));
+	}
+	return lookup_launch(ctx, dst3, d3, phi, d, time + overrideTimeOff, blendAlpha, defo + nv * 4 * t, defo + nv * 4 * tp1, f1,
+	                     f2, vd, sf3, off3, fac, 1, 1);
 }
 
 // ------------------------------------------------------------------ 3D output blur ---------

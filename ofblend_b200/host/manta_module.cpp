@@ -525,12 +525,33 @@ static void requireKind(const GridAny &g, int k, const char *fn, const char *wha
 // LATS: per-ID state of the optimised slice look-up (ref LoadAdvectData :1786-1867).  The whole
 // deformation volume stays resident on the device instead of a cached gz handle + two slices.
 struct Lats {
+	static const int MAXDV = 10;  // ref :1781
 	flof_dim4 dd;
-	void *defo = nullptr;
+	void *defo = nullptr;  // deformation volume 0 (whole file)
 	std::string fname;
-	bool useDefoVols = false;
+	// defo volumes (`thirdload`, ref :1800-1863): further whole files, one window of Tw slices per volume, the one-slice
+	// scratch grid (lats.tmp) and the window-sized scratch of the aligned composition
+	bool useDefoVols = false, doAligned = false;
+	int Tw = 0, lastT = -1, numDv = 0;
+	void *vol[MAXDV] = {}, *win[MAXDV] = {};
+	int filepos[MAXDV];
+	void *vt = nullptr, *dvt = nullptr;
+	void release()
+	{
+		for (int i = 0; i < MAXDV; ++i) {
+			if (vol[i] && vol[i] != defo) flof_free(ctx(), vol[i]);
+			if (win[i]) flof_free(ctx(), win[i]);
+			vol[i] = win[i] = nullptr;
+		}
+		if (defo) flof_free(ctx(), defo);
+		if (vt) flof_free(ctx(), vt);
+		if (dvt) flof_free(ctx(), dvt);
+		defo = vt = dvt = nullptr;
+		numDv = 0;
+	}
 };
 static std::map<int, Lats> g_lats;
+static void *loadDefoVolume(const std::string &fname, const flof_dim4 &dd, const char *fn);
 
 // cache of the hi-res 3D slice sequence of loadPlaceGrid4d, resident on the device
 struct SliceSeq {
@@ -662,6 +683,37 @@ template <class G, class... Extra> static void bind3(py::class_<G, Extra...> &c)
 	    .def("getSize", [](G &g) { V3 v; v.x = (float)g.d.nx; v.y = (float)g.d.ny; v.z = (float)g.d.nz; return v; })
 	    .def("toNumpyBytes", [](G &g) { const std::vector<char> h = g.download(); return py::bytes(h.data(), h.size()); })
 	    .def("fromBytes", [](G &g, const py::bytes &b) { std::string s = b; if (s.size() != g.bytes()) errMsg("fromBytes: size mismatch"); g.upload(s.data()); }, py::arg("data"));
+}
+
+// a whole Vec4 deformation file resident on the device (ref: the reference streams slices of it through a gz handle)
+static void *loadDefoVolume(const std::string &fname, const flof_dim4 &dd, const char *fn)
+{
+	const size_t bytes = (size_t)dd.nx * dd.ny * dd.nz * dd.nt * 16;
+	void *dev = nullptr;
+	CK(flof_malloc(ctx(), &dev, bytes), fn);
+	IoPool::get().waitKey(fname);
+	gzFile gzf = gzopen(fname.c_str(), "rb");
+	if (!gzf) { flof_free(ctx(), dev); errMsg("can't open file " + fname); }
+	char ID4[5] = { 0, 0, 0, 0, 0 };
+	gzread(gzf, ID4, 4);
+	UniHeader head;
+	int dimT = 0;
+	if (strcmp(ID4, "M4T2") || gzread(gzf, &head, sizeof(head)) != (int)sizeof(head) || gzread(gzf, &dimT, 4) != 4) {
+		gzclose(gzf);
+		flof_free(ctx(), dev);
+		errMsg("bad 4d uni file " + fname);
+	}
+	if (head.bytesPerElement != 16) {
+		gzclose(gzf);
+		flof_free(ctx(), dev);
+		errMsg("grid element size doesn't match (Vec4 deformation expected)");
+	}
+	std::vector<char> h(bytes);
+	gzReadAll(gzf, h.data(), bytes, fname);
+	gzclose(gzf);
+	CK(flof_memcpy_h2d(ctx(), dev, h.data(), bytes), fn);
+	CK(flof_sync(ctx()), fn);
+	return dev;
 }
 
 PYBIND11_MODULE(manta, m)
@@ -1003,42 +1055,62 @@ PYBIND11_MODULE(manta, m)
 	// ref loadAdvectTimeSlice_OptInit :1871, _OptAdd :1914, _Finish :1930, _OptRun :1951, loadAdvectTimeSlice :1671
 	m.def("loadAdvectTimeSlice_OptInit",
 	      [](PInt ID, const std::string &fname1, bool useDefoVols, bool doAligned, float partialLoadFac) {
-		      (void)doAligned; (void)partialLoadFac;
+		      const char *fn = "loadAdvectTimeSlice_OptInit";
 		      int x, y, z, t = 0;
 		      uniSize(fname1, x, y, z, &t);
 		      if (x < 1 || y < 1 || z < 1) errMsg("Invalid src size from " + fname1);
 		      debMsg(1, "Found size [" << x << "," << y << "," << z << "]," << t << " in " << fname1);
-		      if (useDefoVols) errMsg("loadAdvectTimeSlice_OptInit: defo volumes (thirdload) are outside the B200 FlOF path (SURVEY 8f-3)");
 		      Lats &l = g_lats[ID.v];
-		      if (l.defo) { flof_free(ctx(), l.defo); l.defo = nullptr; }
+		      const int keepLastT = l.lastT;  // the reference re-uses the LoadAdvectData of an ID (lastT survives, :1883-1886)
+		      l.release();
+		      l.lastT = keepLastT;
 		      l.dd.nx = x; l.dd.ny = y; l.dd.nz = z; l.dd.nt = t;
 		      l.fname = fname1;
-		      const size_t bytes = (size_t)x * y * z * t * 16;
-		      CK(flof_malloc(ctx(), &l.defo, bytes), "loadAdvectTimeSlice_OptInit");
-		      IoPool::get().waitKey(fname1);
-		      gzFile gzf = gzopen(fname1.c_str(), "rb");
-		      if (!gzf) errMsg("can't open file " + fname1);
-		      char ID4[5] = { 0, 0, 0, 0, 0 };
-		      gzread(gzf, ID4, 4);
-		      UniHeader head;
-		      int dimT = 0;
-		      if (strcmp(ID4, "M4T2") || gzread(gzf, &head, sizeof(head)) != (int)sizeof(head) || gzread(gzf, &dimT, 4) != 4) { gzclose(gzf); errMsg("bad 4d uni file " + fname1); }
-		      if (head.bytesPerElement != 16) { gzclose(gzf); errMsg("grid element size doesn't match (Vec4 deformation expected)"); }
-		      std::vector<char> h(bytes);
-		      gzReadAll(gzf, h.data(), bytes, fname1);
-		      gzclose(gzf);
-		      CK(flof_memcpy_h2d(ctx(), l.defo, h.data(), bytes), "loadAdvectTimeSlice_OptInit");
-		      CK(flof_sync(ctx()), "loadAdvectTimeSlice_OptInit");
+		      l.defo = loadDefoVolume(fname1, l.dd, fn);
+		      l.useDefoVols = useDefoVols;
+		      if (useDefoVols) {
+			      // ref :1892-1906: window of int(dimT * max(0.2, partialLoadFac)) slices, zero-initialised grids
+			      const float defoVolWidth = std::max(0.2f, partialLoadFac);
+			      l.Tw = (int)(t * defoVolWidth);
+			      if (l.Tw < 2) errMsg("loadAdvectTimeSlice_OptInit: deformation volume too short for a defo-volume window");
+			      const size_t sb = (size_t)x * y * z * 16;
+			      CK(flof_malloc(ctx(), &l.vt, sb), fn);
+			      CK(flof_malloc(ctx(), &l.dvt, sb * l.Tw), fn);
+			      CK(flof_malloc(ctx(), &l.win[0], sb * l.Tw), fn);
+			      const float zero[4] = { 0.f, 0.f, 0.f, 0.f };
+			      CK(flof_grid_set_const(ctx(), (float *)l.vt, (int64_t)x * y * z, 4, zero), fn);
+			      CK(flof_grid_set_const(ctx(), (float *)l.dvt, (int64_t)x * y * z * l.Tw, 4, zero), fn);
+			      CK(flof_grid_set_const(ctx(), (float *)l.win[0], (int64_t)x * y * z * l.Tw, 4, zero), fn);
+			      l.vol[0] = l.defo;
+			      l.numDv = 1;
+			      l.doAligned = doAligned;
+			      for (int i = 0; i < Lats::MAXDV; ++i) l.filepos[i] = -1;
+			      debMsg(3, "Created defovol solver , " << (int)(t * 0.2) << " , defo0 " << fname1);
+		      }
 	      },
 	      py::arg("ID"), py::arg("fname1"), py::arg("useDefoVols"), py::arg("doAligned"), py::arg("partialLoadFac") = 0.2f);
-	m.def("loadAdvectTimeSlice_OptAdd", [](PInt ID, const std::string &) {
+	m.def("loadAdvectTimeSlice_OptAdd", [](PInt ID, const std::string &fname) {  // ref :1914-1928
+		      const char *fn = "loadAdvectTimeSlice_OptAdd";
 		      auto it = g_lats.find(ID.v);
-		      if (it != g_lats.end() && it->second.useDefoVols) errMsg("loadAdvectTimeSlice_OptAdd: defo volumes are outside the B200 FlOF path");
+		      if (it == g_lats.end() || !it->second.defo) return;
+		      Lats &l = it->second;
+		      if (!l.useDefoVols) return;
+		      if (l.numDv + 1 >= Lats::MAXDV) errMsg("Too many defovolumes loaded!");
+		      int x, y, z, t = 0;
+		      uniSize(fname, x, y, z, &t);
+		      if (x != l.dd.nx || y != l.dd.ny || z != l.dd.nz || t != l.dd.nt) errMsg("grid dim doesn't match in " + fname);
+		      l.vol[l.numDv] = loadDefoVolume(fname, l.dd, fn);
+		      const int64_t wc = (int64_t)x * y * z * l.Tw;
+		      CK(flof_malloc(ctx(), &l.win[l.numDv], (size_t)wc * 16), fn);
+		      const float zero[4] = { 0.f, 0.f, 0.f, 0.f };
+		      CK(flof_grid_set_const(ctx(), (float *)l.win[l.numDv], wc, 4, zero), fn);
+		      l.numDv++;
+		      debMsg(3, "Added defovol " << l.numDv << " file , " << fname);
 	      }, py::arg("ID"), py::arg("fname"));
 	m.def("loadAdvectTimeSlice_Finish", [](PInt ID) {
 		      auto it = g_lats.find(ID.v);
 		      if (it == g_lats.end()) return;
-		      if (it->second.defo) flof_free(ctx(), it->second.defo);
+		      it->second.release();
 		      g_lats.erase(it);
 	      }, py::arg("ID"));
 	m.def("loadAdvectTimeSlice_OptRun",
@@ -1046,27 +1118,77 @@ PYBIND11_MODULE(manta, m)
 	         const py::object &defoScale, const py::object &defoFactor, const py::object &overrideSize, float overrideTimeOff, const py::object &debugVel,
 	         const py::object &debugVelT, bool zeroVel, float thirdAlpha, PInt bordSkip, float fourthAlpha, float defoAniFac) {
 		      const char *fn = "loadAdvectTimeSlice_OptRun";
-		      (void)fname; (void)thirdAlpha; (void)fourthAlpha; (void)debugVel; (void)debugVelT;
+		      (void)fname; (void)debugVel; (void)debugVelT;  // (unused by the reference's optimised variant as well)
 		      auto it = g_lats.find(ID.v);
 		      if (it == g_lats.end() || !it->second.defo) { std::ostringstream s; s << "Load-advect data id " << ID.v << " not initialized!"; errMsg(s.str()); }
+		      Lats &l = it->second;
 		      requireKind(dst, K_REAL, fn, "dst"); requireKind(phi, K_REAL, fn, "phi");
 		      float o[4], s[4], f[4], z[4];
 		      v4arr(toV4(defoOffset), o); v4arr(toV4(defoScale), s); v4arr(toV4(defoFactor), f); v4arr(toV4(overrideSize), z);
+		      if (!l.useDefoVols) {
+			      if (bordSkip.v < 10) debMsg(1, "Warning - dont use for small sizes...");
+			      // zeroVel: vt.setConst(0) (:2091-2094) == scaling the looked-up deformation by 0
+			      CK(flof_load_advect_time_slice(ctx(), (const float *)l.defo, l.dd, dst.f(), dst.d, phi.f(), phi.d, time, blendAlpha,
+			                                     loadTimeScale, o, s, f, z, overrideTimeOff, bordSkip.v, zeroVel ? 0.f : defoAniFac), fn);
+			      return;
+		      }
+		      // ---- defo volumes, ref :2015-2089
+		      if (l.numDv != 2 && l.numDv != 3) errMsg("Code currently only supports 2 deformation volumes");
+		      float srcTime = 0.f, tw = 0.f, sf3[3], off3[3];
+		      int t = 0, tp1 = 0;
+		      flof_lats_source_time(l.dd, phi.d, time, loadTimeScale, o, s, z, &srcTime, &t, &tp1, &tw, sf3, off3);
+		      debMsg(1, "Updating defo vol at " << t << " w " << tw);
+		      const flof_dim4 wd = { l.dd.nx, l.dd.ny, l.dd.nz, l.Tw };
+		      for (int dv = 0; dv < l.numDv; ++dv)
+			      CK(flof_defovol_window_update(ctx(), (float *)l.win[dv], wd, (const float *)l.vol[dv], l.dd.nt, t, l.lastT, (float *)l.vt, &l.filepos[dv]), fn);
+		      const int defovolOff = t - l.Tw / 2;
+		      const float tcoord = srcTime - (float)defovolOff;
+		      CK(flof_defovol_compose(ctx(), (float *)l.vt, (const float *)l.win[0], (const float *)l.win[1], l.numDv == 3 ? (const float *)l.win[2] : nullptr,
+		                              (float *)l.dvt, wd, tcoord, l.doAligned ? 1 : 0, blendAlpha, thirdAlpha, fourthAlpha), fn);
+		      if (zeroVel) {
+			      debMsg(1, "Debug - zeroing deformation!");
+			      const float zero[4] = { 0.f, 0.f, 0.f, 0.f };
+			      CK(flof_grid_set_const(ctx(), (float *)l.vt, (int64_t)l.dd.nx * l.dd.ny * l.dd.nz, 4, zero), fn);
+		      }
+		      l.lastT = t;
 		      if (bordSkip.v < 10) debMsg(1, "Warning - dont use for small sizes...");
-		      // zeroVel: vt.setConst(0) (:2091-2094) == scaling the looked-up deformation by 0
-		      CK(flof_load_advect_time_slice(ctx(), (const float *)it->second.defo, it->second.dd, dst.f(), dst.d, phi.f(), phi.d, time, blendAlpha,
-		                                     loadTimeScale, o, s, f, z, overrideTimeOff, bordSkip.v, zeroVel ? 0.f : defoAniFac), fn);
+		      float fac[4];
+		      for (int c = 0; c < 4; ++c) fac[c] = f[c] * defoAniFac;
+		      const flof_dim3 vd = { l.dd.nx, l.dd.ny, l.dd.nz };
+		      // blendAlpha is already accumulated in vt: the look-up runs with dt = 1 (ref :2087-2088)
+		      CK(flof_lookup_slice4d_with_vel(ctx(), dst.f(), dst.d, phi.f(), phi.d, time + overrideTimeOff, 1.f, (const float *)l.vt, vd, sf3, off3, fac,
+		                                      bordSkip.v), fn);
 	      },
 	      py::arg("ID"), py::arg("fname"), py::arg("dst"), py::arg("phi"), py::arg("time"), py::arg("blendAlpha"), py::arg("loadTimeScale"),
 	      py::arg("defoOffset"), py::arg("defoScale"), py::arg("defoFactor"), py::arg("overrideSize") = py::float_(-1.), py::arg("overrideTimeOff") = 0.f,
 	      py::arg("debugVel") = py::none(), py::arg("debugVelT") = py::none(), py::arg("zeroVel") = false, py::arg("thirdAlpha") = 0.f,
 	      py::arg("bordSkip") = PInt{ 1 }, py::arg("fourthAlpha") = 0.f, py::arg("defoAniFac") = 1.f);
 	m.def("loadAdvectTimeSlice",
-	      [](PInt, const std::string &, Grid3 &, Grid4 &, float, float, float, const py::object &, const py::object &, const py::object &, const py::object &,
-	         float, const py::object &, const py::object &, bool, float, PInt, float, float) {
-		      // The reference's unoptimised twin launches knSemiLagrangeLookupSlice4d as KERNEL(fourd, bnd=1) over a
-		      // one-slice 4D grid, i.e. over t in [1, 0): an empty loop -- dst is left untouched (:1622-1629, :1758).
-		      debMsg(1, "loadAdvectTimeSlice: the reference kernel iterates an empty t-range; dst unchanged (use the _Opt variants)");
+	      [](PInt, const std::string &fname, Grid3 &dst, Grid4 &phi, float time, float blendAlpha, float loadTimeScale, const py::object &defoOffset,
+	         const py::object &defoScale, const py::object &defoFactor, const py::object &overrideSize, float overrideTimeOff, const py::object &debugVel,
+	         const py::object &debugVelT, bool zeroVel, float, PInt, float, float defoAniFac) {
+		      // ref :1671-1760: the slower twin without caching (thirdAlpha / bordSkip / fourthAlpha are not supported there
+		      // either).  knSemiLagrangeLookupSlice4d is KERNEL(fourd, bnd = 1) on a one-slice grid: the generated loop runs
+		      // it as a 3D kernel with t = 0 over the interior cells.
+		      const char *fn = "loadAdvectTimeSlice";
+		      Grid3 *dv = debugVel.is_none() || py::isinstance<py::int_>(debugVel) ? nullptr : debugVel.cast<Grid3 *>();
+		      Grid3 *dt = debugVelT.is_none() || py::isinstance<py::int_>(debugVelT) ? nullptr : debugVelT.cast<Grid3 *>();
+		      requireKind(dst, K_REAL, fn, "dst"); requireKind(phi, K_REAL, fn, "phi");
+		      if (dv) { requireKind(*dv, K_VEC3, fn, "debugVel"); if (dv->d.nx != dst.d.nx || dv->d.ny != dst.d.ny || dv->d.nz != dst.d.nz) errMsg("loadAdvectTimeSlice: debugVel size differs from dst"); }
+		      if (dt) { requireKind(*dt, K_REAL, fn, "debugVelT"); if (dt->d.nx != dst.d.nx || dt->d.ny != dst.d.ny || dt->d.nz != dst.d.nz) errMsg("loadAdvectTimeSlice: debugVelT size differs from dst"); }
+		      int x, y, z, t = 0;
+		      uniSize(fname, x, y, z, &t);
+		      if (x < 1 || y < 1 || z < 1) errMsg("Invalid src size from " + fname);
+		      debMsg(1, "Found size [" << x << "," << y << "," << z << "]," << t << " in " << fname);
+		      flof_dim4 dd = { x, y, z, t };
+		      void *defo = loadDefoVolume(fname, dd, fn);
+		      float o[4], s[4], f[4], zs[4];
+		      v4arr(toV4(defoOffset), o); v4arr(toV4(defoScale), s); v4arr(toV4(defoFactor), f); v4arr(toV4(overrideSize), zs);
+		      const int rc = flof_load_advect_time_slice_unopt(ctx(), (const float *)defo, dd, dst.f(), dst.d, phi.f(), phi.d, time, blendAlpha, loadTimeScale, o, s,
+		                                                       f, zs, overrideTimeOff, defoAniFac, zeroVel ? 1 : 0, dv ? dv->f() : nullptr, dt ? dt->f() : nullptr);
+		      flof_sync(ctx());
+		      flof_free(ctx(), defo);
+		      CK(rc, fn);
 	      },
 	      py::arg("dummyID"), py::arg("fname"), py::arg("dst"), py::arg("phi"), py::arg("time"), py::arg("blendAlpha"), py::arg("loadTimeScale"),
 	      py::arg("defoOffset"), py::arg("defoScale"), py::arg("defoFactor"), py::arg("overrideSize") = py::float_(-1.), py::arg("overrideTimeOff") = 0.f,

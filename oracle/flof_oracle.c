@@ -1250,3 +1250,229 @@ void orc_load_advect_time_slice(const float *defo, orc_dim4 dd, float *dst, int 
 			}
 	free(vt);
 }
+
+/* ---- deformation volumes: optflow4d.cpp:1822-1863 (updateDefoVol), :1951-2105 with useDefoVols ---------------------
+ * vols[dv]: the complete deformation files (dd.nt slices each); the windows and lastT live for the n frames of this call,
+ * exactly like the per-ID LoadAdvectData between _OptInit and _Finish. */
+/* vt: the one-slice scratch grid (lats.tmp) every slice passes through; *filepos: next slice of the re-used gz handle
+ * (fileio.cpp:903-919: once the handle exists, readGrid4dUni ignores the requested slice index and reads the next one;
+ * past the end of the file it reads nothing and vt keeps its content), -1 = not open yet */
+static void orc_defovol_update(float *win, i64 nv4, int Tw, const float *vol, int dimT, int t, int lastT, float *vt,
+                               int *filepos)
+{
+	const int currt = Tw / 2;
+	if (lastT == t) return;
+	if (lastT + 1 == t) {
+		int tl = 0;
+		for (; tl < Tw - 1; ++tl) memcpy(win + nv4 * tl, win + nv4 * (tl + 1), sizeof(float) * nv4);
+		tl = Tw - 1;
+		int it = t - currt + tl;
+		it = it < 0 ? 0 : it;
+		it = it < dimT - 1 ? it : dimT - 1;
+		if (*filepos >= 0) it = *filepos;
+		if (it < dimT) {
+			memcpy(vt, vol + nv4 * it, sizeof(float) * nv4);
+			*filepos = it + 1;
+		} else
+			*filepos = it;
+		memcpy(win + nv4 * tl, vt, sizeof(float) * nv4);
+		return;
+	}
+	for (int tl = 0; tl < Tw; ++tl) {
+		int it = t - currt + tl;
+		it = it < 0 ? 0 : it;
+		it = it < dimT - 1 ? it : dimT - 1;
+		memcpy(vt, vol + nv4 * it, sizeof(float) * nv4);
+		memcpy(win + nv4 * tl, vt, sizeof(float) * nv4);
+	}
+}
+
+void orc_load_advect_defovols(const float *const *vols, int numDv, orc_dim4 dd, int doAligned, float partialLoadFac,
+                              float *dst, int nx, int ny, int nz, const float *phi, orc_dim4 d, int n,
+                              const float *times, float blendAlphaIn, float thirdAlpha, float fourthAlpha,
+                              float loadTimeScale, const float defoOffset[4], const float defoScale[4],
+                              const float defoFactor[4], const float overrideSize[4], float overrideTimeOff,
+                              int bordSkip, float defoAniFac)
+{
+	const int dimT = dd.nt;
+	const float defoVolWidth = 0.2f > partialLoadFac ? 0.2f : partialLoadFac; /* :1893 */
+	const int Tw = (int)(dimT * defoVolWidth);
+	const orc_dim4 wd = { dd.nx, dd.ny, dd.nz, Tw };
+	const i64 nv = (i64)dd.nx * dd.ny * dd.nz, nv4 = nv * 4;
+	float *win[3] = { NULL, NULL, NULL };
+	for (int dv = 0; dv < numDv; ++dv) win[dv] = falloc(nv4 * Tw);
+	float *dvt = doAligned ? falloc(nv4 * Tw) : NULL;
+	float *vt = falloc(nv4);
+	int lastT = -1;
+	int filepos[3] = { -1, -1, -1 };
+	for (int f = 0; f < n; ++f) {
+		const float time = times[f];
+		float blendAlpha = blendAlphaIn;
+		float dim4[4] = { (float)dd.nx, (float)dd.ny, (float)dd.nz, (float)dimT };
+		float defoSize[4] = { (float)d.nx, (float)d.ny, (float)d.nz, (float)d.nt };
+		if (overrideSize[0] > 0.)
+			for (int c = 0; c < 4; ++c) defoSize[c] = (float)(int)overrideSize[c];
+		const float m1[4] = { -1.f, -1.f, -1.f, -1.f };
+		float sourceFactor[4], off2[4] = { defoOffset[0], defoOffset[1], defoOffset[2], defoOffset[3] };
+		orc_grid_factor4d(dim4, defoSize, m1, defoScale, sourceFactor, off2);
+		const float srcTime = (time)*sourceFactor[3] * loadTimeScale + off2[3] - 0.5;
+		int t = (int)srcTime;
+		t = t < dimT - 1 ? t : dimT - 1;
+		/* updateDefoVol(t) */
+		const int defovolOff = t - Tw / 2;
+		for (int dv = 0; dv < numDv; ++dv) orc_defovol_update(win[dv], nv4, Tw, vols[dv], dimT, t, lastT, vt, &filepos[dv]);
+		const float tc = srcTime - defovolOff;
+		if (numDv == 2 && !doAligned) {
+#pragma omp parallel for schedule(static)
+			for (int k = 0; k < dd.nz; ++k)
+				for (int j = 0; j < dd.ny; ++j)
+					for (int i = 0; i < dd.nx; ++i) {
+						const float q[4] = { i + 0.5f, j + 0.5f, k + 0.5f, tc + 0.5f };
+						float v2[4], a[4], r[4];
+						orc_interpol4d(win[1], wd, 4, q, v2);
+						for (int c = 0; c < 4; ++c) r[c] = q[c] - v2[c];
+						orc_interpol4d(win[0], wd, 4, r, a);
+						float *o = vt + 4 * ((i64)i + (i64)dd.nx * (j + (i64)dd.ny * k));
+						for (int c = 0; c < 4; ++c) {
+							const float x = blendAlpha * a[c], y = thirdAlpha * v2[c];
+							o[c] = x + y;
+						}
+					}
+		} else if (numDv == 2) {
+#pragma omp parallel for schedule(static)
+			for (int tl = 0; tl < Tw; ++tl)
+				for (int k = 0; k < dd.nz; ++k)
+					for (int j = 0; j < dd.ny; ++j)
+						for (int i = 0; i < dd.nx; ++i) {
+							const float q[4] = { i + 0.5f, j + 0.5f, k + 0.5f, tl + 0.5f };
+							float v2[4], a[4], r[4];
+							orc_interpol4d(win[1], wd, 4, q, v2);
+							for (int c = 0; c < 4; ++c) r[c] = q[c] - v2[c];
+							orc_interpol4d(win[0], wd, 4, r, a);
+							float *o = dvt + 4 * ((i64)i + (i64)dd.nx * (j + (i64)dd.ny * (k + (i64)dd.nz * tl)));
+							for (int c = 0; c < 4; ++c) {
+								const float x = blendAlpha * a[c], y = thirdAlpha * v2[c];
+								o[c] = x + y;
+							}
+						}
+#pragma omp parallel for schedule(static)
+			for (int k = 0; k < dd.nz; ++k)
+				for (int j = 0; j < dd.ny; ++j)
+					for (int i = 0; i < dd.nx; ++i) {
+						const float q[4] = { i + 0.5f, j + 0.5f, k + 0.5f, tc + 0.5f };
+						float v1[4], r[4];
+						orc_interpol4d(win[0], wd, 4, q, v1);
+						for (int c = 0; c < 4; ++c) {
+							const float neg = v1[c] * -1;                       /* invert! */
+							const float s = (float)((1. - blendAlpha) * neg);    /* double scalar * float component */
+							r[c] = q[c] - s;
+						}
+						orc_interpol4d(dvt, wd, 4, r, vt + 4 * ((i64)i + (i64)dd.nx * (j + (i64)dd.ny * k)));
+					}
+		} else { /* numDv == 3 */
+#pragma omp parallel for schedule(static)
+			for (int k = 0; k < dd.nz; ++k)
+				for (int j = 0; j < dd.ny; ++j)
+					for (int i = 0; i < dd.nx; ++i) {
+						const float q[4] = { i + 0.5f, j + 0.5f, k + 0.5f, tc + 0.5f };
+						float v3[4], v2[4], v1[4], r[4], r2[4];
+						orc_interpol4d(win[2], wd, 4, q, v3);
+						for (int c = 0; c < 4; ++c) r[c] = q[c] - v3[c];
+						orc_interpol4d(win[1], wd, 4, r, v2);
+						for (int c = 0; c < 4; ++c) r2[c] = r[c] - v2[c];
+						orc_interpol4d(win[0], wd, 4, r2, v1);
+						float *o = vt + 4 * ((i64)i + (i64)dd.nx * (j + (i64)dd.ny * k));
+						for (int c = 0; c < 4; ++c) {
+							const float x = blendAlpha * v1[c], y = thirdAlpha * v2[c], z = fourthAlpha * v3[c];
+							const float xy = x + y;
+							o[c] = xy + z;
+						}
+					}
+		}
+		blendAlpha = 1.; /* :2088 already accumulated in vt */
+		lastT = t;
+		float fac[4];
+		for (int c = 0; c < 4; ++c) fac[c] = defoFactor[c] * defoAniFac;
+		const float tm = time + overrideTimeOff;
+		const float dt = blendAlpha;
+		const int b = bordSkip > 10 ? bordSkip : 10;
+		float *out = dst + (i64)f * nx * ny * nz;
+#pragma omp parallel for schedule(static)
+		for (int k = b; k < nz - b; ++k)
+			for (int j = b; j < ny - b; ++j)
+				for (int i = b; i < nx - b; ++i) {
+					const float p3[3] = { (float)i * sourceFactor[0] + off2[0], (float)j * sourceFactor[1] + off2[1],
+						                  (float)k * sourceFactor[2] + off2[2] };
+					float v[4];
+					orc_interpol3d(vt, dd.nx, dd.ny, dd.nz, 4, p3, v);
+					for (int c = 0; c < 4; ++c) v[c] *= fac[c];
+					const float p4[4] = { (i + 0.5f) - v[0] * dt, (j + 0.5f) - v[1] * dt, (k + 0.5f) - v[2] * dt,
+						                  (tm + 0.5f) - v[3] * dt };
+					orc_interpol4d(phi, d, 1, p4, out + ((i64)i + (i64)nx * j + (i64)nx * ny * k));
+				}
+	}
+	for (int dv = 0; dv < numDv; ++dv) free(win[dv]);
+	free(dvt);
+	free(vt);
+}
+
+/* optflow4d.cpp:1671-1760: the unoptimised loadAdvectTimeSlice -- the time-blended deformation slice, re-interpolated to
+ * the output size (interior cells, bnd 1; vdst is cleared first) and scaled, returned as dbgVel (3 floats per cell) /
+ * dbgVelT (either may be NULL), then knSemiLagrangeLookupSlice4d :1622-1629 over the interior cells of dst (the
+ * generated KERNEL(fourd, bnd = 1) code runs a one-slice grid as a 3D kernel with t = 0). */
+void orc_load_advect_time_slice_unopt(const float *defo, orc_dim4 dd, float *dst, float *dbgVel, float *dbgVelT, int nx,
+                                      int ny, int nz, const float *phi, orc_dim4 d, float time, float blendAlpha,
+                                      float loadTimeScale, const float defoOffset[4], const float defoScale[4],
+                                      const float defoFactor[4], const float overrideSize[4], float overrideTimeOff,
+                                      float defoAniFac, int zeroVel)
+{
+	const int dimT = dd.nt;
+	float dim4[4] = { (float)dd.nx, (float)dd.ny, (float)dd.nz, (float)dimT };
+	float defoSize[4] = { (float)d.nx, (float)d.ny, (float)d.nz, (float)d.nt };
+	if (overrideSize[0] > 0.)
+		for (int c = 0; c < 4; ++c) defoSize[c] = (float)(int)overrideSize[c];
+	const float m1[4] = { -1.f, -1.f, -1.f, -1.f };
+	float sourceFactor[4], off2[4] = { defoOffset[0], defoOffset[1], defoOffset[2], defoOffset[3] };
+	orc_grid_factor4d(dim4, defoSize, m1, defoScale, sourceFactor, off2);
+	const float srcTime = (time)*sourceFactor[3] * loadTimeScale + off2[3] - 0.5;
+	int t = (int)srcTime;
+	int tp1 = t + 1;
+	const float tw = srcTime - (float)t;
+	t = t < dimT - 1 ? t : dimT - 1;
+	tp1 = tp1 < dimT - 1 ? tp1 : dimT - 1;
+	const i64 nv = (i64)dd.nx * dd.ny * dd.nz;
+	const float *s1 = defo + nv * 4 * t, *s2 = defo + nv * 4 * tp1;
+	float *v1 = falloc(nv * 4);
+	const float f1 = 1. - tw, f2 = tw;
+	for (i64 i = 0; i < nv * 4; ++i) { /* v1.multConst(1-tw); v2.multConst(tw); v1.add(v2) */
+		const float a = s1[i] * f1, b = s2[i] * f2;
+		v1[i] = zeroVel ? 0.f : a + b;
+	}
+	for (i64 c = 0; c < (i64)nx * ny * nz; ++c) {
+		if (dbgVel) dbgVel[3 * c] = dbgVel[3 * c + 1] = dbgVel[3 * c + 2] = 0.f;
+		if (dbgVelT) dbgVelT[c] = 0.f;
+	}
+	for (int k = 1; k < nz - 1; ++k)
+		for (int j = 1; j < ny - 1; ++j)
+			for (int i = 1; i < nx - 1; ++i) {
+				const float p3[3] = { (float)i * sourceFactor[0] + off2[0], (float)j * sourceFactor[1] + off2[1],
+					                  (float)k * sourceFactor[2] + off2[2] };
+				float v[4];
+				orc_interpol3d(v1, dd.nx, dd.ny, dd.nz, 4, p3, v);
+				for (int c = 0; c < 4; ++c) v[c] *= defoFactor[c] * defoAniFac;
+				const i64 o = (i64)i + (i64)nx * (j + (i64)ny * k);
+				if (dbgVel) {
+					dbgVel[3 * o] = v[0];
+					dbgVel[3 * o + 1] = v[1];
+					dbgVel[3 * o + 2] = v[2];
+				}
+				if (dbgVelT) dbgVelT[o] = v[3];
+				if (dst) {
+					const float tm = time + overrideTimeOff, dt = blendAlpha;
+					const float p4[4] = { (i + 0.5f) - v[0] * dt, (j + 0.5f) - v[1] * dt, (k + 0.5f) - v[2] * dt,
+						                  (tm + 0.5f) - v[3] * dt };
+					orc_interpol4d(phi, d, 1, p4, dst + o);
+				}
+			}
+	free(v1);
+}

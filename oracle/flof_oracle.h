@@ -120,6 +120,19 @@ void orc_load_advect_time_slice(const float *defo, orc_dim4 dd, float *dst, int 
                                 const float defoFactor[4], const float overrideSize[4],
                                 float overrideTimeOff, int bordSkip, float defoAniFac);
 
+/* optflow4d.cpp:1822-1863, 1951-2105 with useDefoVols: n frames through 2 / 3 deformation volumes */
+void orc_load_advect_defovols(const float *const *vols, int numDv, orc_dim4 dd, int doAligned, float partialLoadFac,
+                              float *dst, int nx, int ny, int nz, const float *phi, orc_dim4 d, int n,
+                              const float *times, float blendAlpha, float thirdAlpha, float fourthAlpha,
+                              float loadTimeScale, const float defoOffset[4], const float defoScale[4],
+                              const float defoFactor[4], const float overrideSize[4], float overrideTimeOff,
+                              int bordSkip, float defoAniFac);
+/* optflow4d.cpp:1671-1760: the unoptimised loadAdvectTimeSlice incl. its debugVel / debugVelT outputs */
+void orc_load_advect_time_slice_unopt(const float *defo, orc_dim4 dd, float *dst, float *dbgVel, float *dbgVelT, int nx,
+                                      int ny, int nz, const float *phi, orc_dim4 d, float time, float blendAlpha,
+                                      float loadTimeScale, const float defoOffset[4], const float defoScale[4],
+                                      const float defoFactor[4], const float overrideSize[4], float overrideTimeOff,
+                                      float defoAniFac, int zeroVel);
 #ifdef __cplusplus
 }
 #endif

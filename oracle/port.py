@@ -307,6 +307,39 @@ def load_advect_time_slice(defo, d3, phi, time, blendAlpha, loadTimeScale, defoO
     return out
 
 
+def load_advect_defovols(vols, d3, phi, times, blendAlpha, thirdAlpha, fourthAlpha, loadTimeScale, defoOffset, defoScale,
+                         defoFactor, doAligned=False, partialLoadFac=0.2, overrideSize=-1., overrideTimeOff=0.,
+                         bordSkip=1, defoAniFac=1.):
+    """loadAdvectTimeSlice_OptInit(useDefoVols=True) + _OptAdd + n x _OptRun (ref optflow4d.cpp:1822-1863, 1951-2105);
+    vols: 2 or 3 complete deformation volumes (Vec4)."""
+    vols = [_f32(v) for v in vols]
+    p = _f32(phi)
+    times = np.ascontiguousarray(times, np.float32)
+    out = np.zeros((len(times), d3[2], d3[1], d3[0]), np.float32)
+    arr = (C.c_void_p * 3)(*([v.ctypes.data for v in vols] + [None] * (3 - len(vols))))
+    lib().orc_load_advect_defovols(
+        arr, len(vols), _d(dims_of(vols[0])), int(bool(doAligned)), C.c_float(partialLoadFac), _p(out), int(d3[0]), int(d3[1]),
+        int(d3[2]), _p(p), _d(dims_of(p)), len(times), _p(times), C.c_float(blendAlpha), C.c_float(thirdAlpha),
+        C.c_float(fourthAlpha), C.c_float(loadTimeScale), _f4(defoOffset), _f4(defoScale), _f4(defoFactor), _f4(overrideSize),
+        C.c_float(overrideTimeOff), int(bordSkip), C.c_float(defoAniFac))
+    return out
+
+
+def load_advect_time_slice_unopt(defo, d3, phi, time, blendAlpha, loadTimeScale, defoOffset, defoScale, defoFactor,
+                                 overrideSize=-1., overrideTimeOff=0., defoAniFac=1., zeroVel=False, dst=None):
+    """The unoptimised loadAdvectTimeSlice (ref optflow4d.cpp:1671-1760): returns (dst, debugVel (Vec3), debugVelT)."""
+    defo = _f32(defo)
+    p = _f32(phi)
+    out = np.zeros((d3[2], d3[1], d3[0]), np.float32) if dst is None else _f32(dst).copy()
+    dv = np.zeros((d3[2], d3[1], d3[0], 3), np.float32)
+    dt = np.zeros((d3[2], d3[1], d3[0]), np.float32)
+    lib().orc_load_advect_time_slice_unopt(
+        _p(defo), _d(dims_of(defo)), _p(out), _p(dv), _p(dt), int(d3[0]), int(d3[1]), int(d3[2]), _p(p), _d(dims_of(p)),
+        C.c_float(time), C.c_float(blendAlpha), C.c_float(loadTimeScale), _f4(defoOffset), _f4(defoScale), _f4(defoFactor),
+        _f4(overrideSize), C.c_float(overrideTimeOff), C.c_float(defoAniFac), int(bool(zeroVel)))
+    return out, dv, dt
+
+
 def dot_seq(a, b, kind=0, diag=0.0):
     """The reference's sequential dot-product loop (dotProd, optflow4d.cpp:234-241) on Vec4 arrays; kind 1 applies the
     Jacobi preconditioner of grad = b first (precondApply :345-351)."""

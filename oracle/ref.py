@@ -341,6 +341,35 @@ def load_advect_time_slices_opt(fname, d3, phi, times, blendAlpha, loadTimeScale
     return out
 
 
+def load_advect_defovols(fnames, d3, phi, times, blendAlpha, thirdAlpha, fourthAlpha, loadTimeScale, defoOffset, defoScale,
+                         defoFactor, doAligned=False, partialLoadFac=0.2, overrideSize=-1., overrideTimeOff=0.,
+                         bordSkip=1, defoAniFac=1.):
+    """The reference's _OptInit(useDefoVols=True) + _OptAdd per further file + n x _OptRun + _Finish; fnames: .uni files."""
+    p = _f32(phi)
+    times = np.ascontiguousarray(times, np.float32)
+    out = np.zeros((len(times), d3[2], d3[1], d3[0]), np.float32)
+    names = (C.c_char_p * 3)(*([f.encode() for f in fnames] + [None] * (3 - len(fnames))))
+    _chk(lib().ref_load_advect_defovols(
+        names, len(fnames), int(bool(doAligned)), C.c_float(partialLoadFac), _i4(d3), _p(out), _i4(dims_of(p)), _p(p),
+        len(times), _p(times), C.c_float(blendAlpha), C.c_float(thirdAlpha), C.c_float(fourthAlpha),
+        C.c_float(loadTimeScale), _f4(defoOffset), _f4(defoScale), _f4(defoFactor), _f4(overrideSize),
+        C.c_float(overrideTimeOff), int(bordSkip), C.c_float(defoAniFac)))
+    return out
+
+
+def load_advect_time_slice_unopt(fname, d3, phi, time, blendAlpha, loadTimeScale, defoOffset, defoScale, defoFactor,
+                                 overrideSize=-1., overrideTimeOff=0., defoAniFac=1., zeroVel=False):
+    p = _f32(phi)
+    out = np.zeros((d3[2], d3[1], d3[0]), np.float32)
+    dv = np.zeros((d3[2], d3[1], d3[0], 3), np.float32)
+    dt = np.zeros((d3[2], d3[1], d3[0]), np.float32)
+    _chk(lib().ref_load_advect_time_slice_debug(
+        fname.encode(), _i4(d3), _p(out), _p(dv), _p(dt), _i4(dims_of(p)), _p(p), C.c_float(time), C.c_float(blendAlpha),
+        C.c_float(loadTimeScale), _f4(defoOffset), _f4(defoScale), _f4(defoFactor), _f4(overrideSize),
+        C.c_float(overrideTimeOff), C.c_float(defoAniFac), int(bool(zeroVel))))
+    return out, dv, dt
+
+
 def load_advect_time_slice(fname, d3, phi, time, blendAlpha, loadTimeScale, defoOffset,
                            defoScale, defoFactor, overrideSize=-1., overrideTimeOff=0.):
     p = _f32(phi)

@@ -666,7 +666,65 @@ int ref_load_advect_time_slices_opt(const char *fname, const int *d3,
 	REF_CATCH
 }
 
+/* optflow4d.cpp:1871 _OptInit(useDefoVols = true) + :1914 _OptAdd per further file + n x :1951 _OptRun + :1930 _Finish:
+ * 2 or 3 deformation volumes composed per frame (flof.py `thirdload`). */
+int ref_load_advect_defovols(const char *const *fnames, int numDv, int doAligned,
+                             float partialLoadFac, const int *d3, float *dst,
+                             const int *d, const float *phi, int n,
+                             const float *times, float blendAlpha,
+                             float thirdAlpha, float fourthAlpha,
+                             float loadTimeScale, const float *defoOffset,
+                             const float *defoScale, const float *defoFactor,
+                             const float *overrideSize, float overrideTimeOff,
+                             int bordSkip, float defoAniFac)
+{
+	REF_TRY
+	SOLVER(d);
+	Grid4d<Real> p(&solver);
+	put(p, phi);
+	FluidSolver s3(Vec3i(d3[0], d3[1], d3[2]), 3, 1);
+	Grid<Real> out(&s3);
+	const int ID = 4712;
+	loadAdvectTimeSlice_OptInit(ID, fnames[0], true, doAligned != 0, partialLoadFac);
+	for (int dv = 1; dv < numDv; ++dv) loadAdvectTimeSlice_OptAdd(ID, fnames[dv]);
+	for (int f = 0; f < n; ++f) {
+		out.clear();
+		loadAdvectTimeSlice_OptRun(ID, fnames[0], out, p, times[f], blendAlpha,
+		                           loadTimeScale, v4(defoOffset),
+		                           v4(defoScale), v4(defoFactor),
+		                           v4(overrideSize), overrideTimeOff, NULL,
+		                           NULL, false, thirdAlpha, bordSkip, fourthAlpha, defoAniFac);
+		get3(out, dst + (size_t)f * cells3(out));
+	}
+	loadAdvectTimeSlice_Finish(ID);
+	REF_CATCH
+}
+
 /* optflow4d.cpp:1671 loadAdvectTimeSlice (unoptimised twin, one frame) */
+int ref_load_advect_time_slice_debug(const char *fname, const int *d3, float *dst, float *dbgVel, float *dbgVelT,
+                                     const int *d, const float *phi, float time, float blendAlpha, float loadTimeScale,
+                                     const float *defoOffset, const float *defoScale, const float *defoFactor,
+                                     const float *overrideSize, float overrideTimeOff, float defoAniFac, int zeroVel)
+{
+	REF_TRY
+	SOLVER(d);
+	Grid4d<Real> p(&solver);
+	put(p, phi);
+	FluidSolver s3(Vec3i(d3[0], d3[1], d3[2]), 3, 1);
+	Grid<Real> out(&s3), velT(&s3);
+	Grid<Vec3> vel(&s3);
+	loadAdvectTimeSlice(0, fname, out, p, time, blendAlpha, loadTimeScale, v4(defoOffset), v4(defoScale), v4(defoFactor),
+	                    v4(overrideSize), overrideTimeOff, &vel, &velT, zeroVel != 0, 0., 1, 0., defoAniFac);
+	get3(out, dst);
+	get3(velT, dbgVelT);
+	for (size_t c = 0; c < cells3(out); ++c) {
+		dbgVel[3 * c] = vel[c].x;
+		dbgVel[3 * c + 1] = vel[c].y;
+		dbgVel[3 * c + 2] = vel[c].z;
+	}
+	REF_CATCH
+}
+
 int ref_load_advect_time_slice(const char *fname, const int *d3, float *dst,
                                const int *d, const float *phi, float time,
                                float blendAlpha, float loadTimeScale,

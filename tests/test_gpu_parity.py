@@ -205,6 +205,43 @@ def test_mode3_loaders(gpu):
            port.load_advect_time_slice(defo, big[:3], phi, tm, 0.5, 1., 0., 1., fac, big, 0., 4, 1.))
 
 
+@pytest.mark.parametrize("case", ["two", "two_aligned", "three", "two_eof"])
+def test_defo_volumes_bitexact(gpu, case):
+    """`thirdload`: two / three deformation volumes composed per output frame -- window refresh (all three
+    branches of updateDefoVol incl. the re-used file handle), the compositions of ref optflow4d.cpp:2015-2089 and the slice
+    look-up, through flof_defovol_window_update / flof_defovol_compose / flof_lookup_slice4d_with_vel; bit-exact against
+    the oracle (which tests/test_oracle_vs_ref.py pins to the reference on the same cases)."""
+    dd = (8, 7, 8, 20)
+    vols = [rnd((dd[3], dd[2], dd[1], dd[0], 4), 30 + q, 0.5) for q in range(3 if case == "three" else 2)]
+    big = (30, 28, 30, 30)
+    phi = rnd((big[3], big[2], big[1], big[0]), 41)
+    fac = tuple(big[i] / dd[i] for i in range(4))
+    times = [0.9, 1.2, 2.4, 3.6, 3.7, 14.5, 16., 29.]
+    if case == "two_eof":
+        times = [24.55, 26.2, 27.85, 29.05]
+    kw = dict(doAligned=(case == "two_aligned"), partialLoadFac=0.1, overrideSize=big, overrideTimeOff=0.5, bordSkip=3,
+              defoAniFac=0.75)
+    a = gpu.load_advect_defovols(vols, big[:3], phi, times, 0.6, 0.3, 0.2, 1., 0., 1., fac, **kw)
+    b = port.load_advect_defovols(vols, big[:3], phi, times, 0.6, 0.3, 0.2, 1., 0., 1., fac, **kw)
+    eq(a, b)
+    assert np.abs(b).max() > 0
+
+
+def test_unoptimised_load_advect_time_slice(gpu):
+    """loadAdvectTimeSlice, the slower twin (ref optflow4d.cpp:1671-1760): dst over the interior cells (bnd 1) and the
+    debugVel / debugVelT outputs, bit-exact against the oracle (pinned to the reference in tests/test_oracle_vs_ref.py)."""
+    dd = (8, 9, 7, 12)
+    defo = rnd((dd[3], dd[2], dd[1], dd[0], 4), 51, 0.6)
+    big = (21, 19, 20, 30)
+    phi = rnd((big[3], big[2], big[1], big[0]), 52)
+    fac = tuple(big[i] / dd[i] for i in range(4))
+    for tm, zero in ((6.5, False), (11.25, False), (29., False), (8., True)):
+        a = gpu.load_advect_time_slice_unopt(defo, big[:3], phi, tm, 0.7, 1., 0., 1., fac, big, -0.5, 0.8, zero)
+        b = port.load_advect_time_slice_unopt(defo, big[:3], phi, tm, 0.7, 1., 0., 1., fac, big, -0.5, 0.8, zero)
+        for x, y in zip(a, b):
+            eq(x, y)
+
+
 def test_multiscale_small(gpu):
     """Full V-cycle (2 levels, 3 steps, final projection) against the oracle."""
     d = (24, 24, 24, 20)

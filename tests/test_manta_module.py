@@ -84,3 +84,71 @@ def test_helper_plugins_match_reference_semantics():
     host = os.path.join(ROOT, "ofblend_b200", "host")
     p = subprocess.run([sys.executable, "-c", SNIPPET, host], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode == 0 and "MANTA_HELPERS_OK" in p.stdout, p.stdout[-2000:] + "\n" + p.stderr[-3000:]
+
+
+DEFOVOL_SNIPPET = r"""
+import os, sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+tmp = sys.argv[3]
+from manta import *
+from oracle import port   # checker only
+rng = np.random.default_rng(5)
+dd = (8, 7, 8, 20)
+big = (30, 28, 30, 30)
+
+def put(g, a):
+    g.fromBytes(np.ascontiguousarray(a).tobytes())
+
+def get(g, shape, dt=np.float32):
+    return np.frombuffer(g.toNumpyBytes(), dtype=dt).reshape(shape)
+
+sd = Solver(name="defo", gridSize=vec3(dd[0], dd[1], dd[2]), dim=3, fourthDim=dd[3])
+vols, fns = [], []
+for q in range(3):
+    V = (rng.standard_normal((dd[3], dd[2], dd[1], dd[0], 4)) * 0.5).astype(np.float32)
+    g = sd.create(Grid4Vec4); put(g, V)
+    fn = os.path.join(tmp, "defo%d.uni" % q); g.save(fn)
+    vols.append(V); fns.append(fn)
+flushUniWrites()
+sb = Solver(name="big", gridSize=vec3(big[0], big[1], big[2]), dim=3, fourthDim=big[3])
+s3 = Solver(name="out", gridSize=vec3(big[0], big[1], big[2]), dim=3)
+PHI = rng.standard_normal((big[3], big[2], big[1], big[0])).astype(np.float32)
+phi = sb.create(Grid4Real); put(phi, PHI)
+dst = s3.create(RealGrid)
+fac = vec4(*[big[i] / dd[i] for i in range(4)])
+facn = tuple(big[i] / dd[i] for i in range(4))
+osz = vec4(*[float(x) for x in big])
+times = [0.9, 2.4, 3.6, 14.5, 16., 29.]
+sh3 = (big[2], big[1], big[0])
+for n, aligned in ((2, False), (2, True), (3, False)):
+    loadAdvectTimeSlice_OptInit(7, fns[0], True, aligned, 0.1)
+    for q in range(1, n):
+        loadAdvectTimeSlice_OptAdd(7, fns[q])
+    want = port.load_advect_defovols(vols[:n], big[:3], PHI, times, 0.6, 0.3, 0.2, 1., 0., 1., facn, doAligned=aligned,
+                                     partialLoadFac=0.1, overrideSize=big, overrideTimeOff=0.5, bordSkip=3, defoAniFac=0.75)
+    for f, tm in enumerate(times):
+        dst.setConst(0.)
+        loadAdvectTimeSlice_OptRun(7, fns[0], dst, phi, tm, 0.6, 1., vec4(0.), vec4(1.), fac, overrideSize=osz, overrideTimeOff=0.5,
+                                   thirdAlpha=0.3, bordSkip=3, fourthAlpha=0.2, defoAniFac=0.75)
+        got = get(dst, sh3)
+        assert np.array_equal(got, want[f]), (n, aligned, f, np.abs(got - want[f]).max())
+    loadAdvectTimeSlice_Finish(7)
+# the unoptimised twin with its debug outputs
+dv, dt = s3.create(VecGrid), s3.create(RealGrid)
+dst.setConst(0.)
+loadAdvectTimeSlice(0, fns[0], dst, phi, 6.5, 0.7, 1., vec4(0.), vec4(1.), fac, overrideSize=osz, overrideTimeOff=-0.5, debugVel=dv, debugVelT=dt,
+                    defoAniFac=0.8)
+w = port.load_advect_time_slice_unopt(vols[0], big[:3], PHI, 6.5, 0.7, 1., 0., 1., facn, big, -0.5, 0.8, False)
+assert np.array_equal(get(dst, sh3), w[0]) and np.abs(w[0]).max() > 0
+assert np.array_equal(get(dv, sh3 + (3,)), w[1]) and np.array_equal(get(dt, sh3), w[2])
+print("MANTA_DEFOVOL_OK")
+"""
+
+
+def test_defo_volumes_and_unoptimised_lookup_through_the_module(tmp_path):
+    """`thirdload` through the plugin API exactly as flof.py would drive it (ref flof.py:757-816): _OptInit(useDefoVols=True),
+    _OptAdd, _OptRun with thirdAlpha / fourthAlpha, _Finish; files written by the module itself; frames compared bit for bit
+    with the oracle.  Also loadAdvectTimeSlice with debugVel / debugVelT."""
+    host = os.path.join(ROOT, "ofblend_b200", "host")
+    p = subprocess.run([sys.executable, "-c", DEFOVOL_SNIPPET, host, ROOT, str(tmp_path)], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0 and "MANTA_DEFOVOL_OK" in p.stdout, p.stdout[-2000:] + "\n" + p.stderr[-3000:]

@@ -202,3 +202,50 @@ def test_load_place_and_lookup(tmp_path):
         o = port.load_advect_time_slice(defo, big[:3], phi, tm, 0.5, 1., 0., 1., fac, big, 0., 4, 1.)
         eq(o, outs[f])
     assert np.abs(outs).max() > 0
+
+
+@pytest.mark.parametrize("case", ["two", "two_aligned", "three", "two_eof"])
+def test_defo_volumes_two_and_three(tmp_path, case):
+    """`thirdload`: loadAdvectTimeSlice_OptInit(useDefoVols=True) + _OptAdd + _OptRun (ref optflow4d.cpp:1822-1863 window
+    refresh incl. its start-up quirk, :2015-2089 compositions) -- oracle bit-exact against the reference, frame by frame.
+    The time list exercises all three refresh branches: first call at t = 0 (only the last window slice gets filled),
+    same t, t + 1, and a jump."""
+    dd = (8, 7, 8, 20)                                   # dimT 20 -> window of int(20 * 0.2) = 4 slices
+    vols = [rnd((dd[3], dd[2], dd[1], dd[0], 4), 30 + q, 0.5) for q in range(3 if case == "three" else 2)]
+    fns = []
+    for q, v in enumerate(vols):
+        fns.append(os.path.join(str(tmp_path), "defo_%s_%d.uni" % (case, q)))
+        ref.grid4d_save(v, fns[-1])
+    big = (30, 28, 30, 30)
+    phi = rnd((big[3], big[2], big[1], big[0]), 41)
+    fac = tuple(big[i] / dd[i] for i in range(4))
+    times = [0.9, 1.2, 2.4, 3.6, 3.7, 14.5, 16., 29.]
+    if case == "two_eof":   # t = 16 (all), 17, 18, 19 one slice at a time: the re-used file handle runs past the last slice
+        times = [24.55, 26.2, 27.85, 29.05]
+    kw = dict(doAligned=(case == "two_aligned"), partialLoadFac=0.1, overrideSize=big, overrideTimeOff=0.5, bordSkip=3,
+              defoAniFac=0.75)
+    a = port.load_advect_defovols(vols, big[:3], phi, times, 0.6, 0.3, 0.2, 1., 0., 1., fac, **kw)
+    b = ref.load_advect_defovols(fns, big[:3], phi, times, 0.6, 0.3, 0.2, 1., 0., 1., fac, **kw)
+    eq(a, b)
+    assert np.abs(b).max() > 0
+    assert not np.array_equal(b[0], b[2])
+
+
+def test_unoptimised_load_advect_time_slice(tmp_path):
+    """The slower twin loadAdvectTimeSlice (ref optflow4d.cpp:1671-1760) with its debugVel / debugVelT outputs.  Its
+    look-up kernel is KERNEL(fourd, bnd = 1) on a ONE-slice 4D grid: the generated loop runs it as a 3D kernel with t = 0
+    over the interior cells, so dst is written everywhere but on the outer shell."""
+    dd = (8, 9, 7, 12)
+    defo = rnd((dd[3], dd[2], dd[1], dd[0], 4), 51, 0.6)
+    fn = os.path.join(str(tmp_path), "defo_dbg.uni")
+    ref.grid4d_save(defo, fn)
+    big = (21, 19, 20, 30)
+    phi = rnd((big[3], big[2], big[1], big[0]), 52)
+    fac = tuple(big[i] / dd[i] for i in range(4))
+    for tm, zero in ((6.5, False), (11.25, False), (29., False), (8., True)):
+        a = port.load_advect_time_slice_unopt(defo, big[:3], phi, tm, 0.7, 1., 0., 1., fac, big, -0.5, 0.8, zero)
+        b = ref.load_advect_time_slice_unopt(fn, big[:3], phi, tm, 0.7, 1., 0., 1., fac, big, -0.5, 0.8, zero)
+        for x, y in zip(a, b):
+            eq(x, y)
+        assert np.abs(b[0]).max() > 0
+    assert np.abs(b[1]).max() == 0 and np.abs(a[2]).max() == 0     # zeroVel
