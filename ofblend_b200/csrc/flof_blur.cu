@@ -172,8 +172,9 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 	int mode = ctx->opt.expol_mode;
 	if (mode < 0) mode = flof_cells(d) >= ((int64_t)1 << 25) ? 4 : 3;
 	const int64_t cap4 = mode == 0 ? flof_expol_planes_capacity(ctx, d) : 0;
-	const int tz = mode == 4 ? 4 : 2;
-	const int64_t capz = (mode == 3 || mode == 4) ? flof_expol_zn_capacity(ctx, d, tz) : 0;  // 3 / 4: Vec4 work list with 4y x 2z / 4y x 4z items
+	const int tz = (mode == 4 || mode == 6) ? 4 : 2;  // 5 / 6: like 3 / 4, the x-neighbour columns come from lane shuffles
+	const int shfl = mode >= 5 ? 1 : 0;
+	const int64_t capz = mode >= 3 ? flof_expol_zn_capacity(ctx, d, tz) : 0;  // 3 / 4: Vec4 work list with 4y x 2z / 4y x 4z items
 	const int64_t cap1 = ((mode <= 1 || mode >= 3) && cap4 == 0 && capz == 0) ? flof_expol_item_capacity(ctx, d) : 0;
 	void *tmp = NULL, *tmp2 = NULL, *items = NULL, *count = NULL;
 	int rc = flof_tmp_alloc(ctx, &tmp, bytes, false);
@@ -209,7 +210,7 @@ extern "C" int flof_cv_expol_blur4d(flof_ctx *ctx, float *a, const float *marker
 			rc = flof_halo_exchange(ctx, cur, d.nt, slice_bytes, 1);
 			if (rc != FLOF_OK) break;
 			if (capz > 0)
-				rc = flof_launch_expol_zn(ctx, cur, oth, (const uint2 *)items, n, d, tz);
+				rc = flof_launch_expol_zn(ctx, cur, oth, (const uint2 *)items, n, d, tz, shfl);
 			else if (cap1 > 0)
 				rc = flof_launch_expol_items(ctx, cur, oth, (const uint32_t *)items, n, d);
 			else

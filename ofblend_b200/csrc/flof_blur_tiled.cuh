@@ -484,6 +484,101 @@ __global__ void __launch_bounds__(FLOF_BLOCK, MINB)
 	}
 }
 
+// Shuffle variant of the same items: a lane loads only its OWN column of a row (one aligned, fully coalesced request per
+// warp where the items are x-neighbours) and takes the x-1 / x+1 columns from the neighbouring lanes -- the list keeps the
+// items of a row x-ordered and the cells that change form compact regions, so almost every lane has both neighbours next
+// to it; a lane without one loads that column itself.  The L1 data pipe charges ~2 cycles per 128-byte line a request
+// touches: three overlapping requests per row cost 4 + 5 + 5 lines, one aligned request 4 (plus the few lines of the
+// predicated edge loads).  Arithmetic and tap order are unchanged.
+__device__ __forceinline__ p4 p4_shfl_up(const p4 &v)
+{
+	p4 r;
+	r.lo = __shfl_up_sync(0xffffffffu, v.lo, 1);
+	r.hi = __shfl_up_sync(0xffffffffu, v.hi, 1);
+	return r;
+}
+__device__ __forceinline__ p4 p4_shfl_down(const p4 &v)
+{
+	p4 r;
+	r.lo = __shfl_down_sync(0xffffffffu, v.lo, 1);
+	r.hi = __shfl_down_sync(0xffffffffu, v.hi, 1);
+	return r;
+}
+template <int TZ, int MINB>
+__global__ void __launch_bounds__(FLOF_BLOCK, MINB)
+    k_cv_expol_items_zs(const float4 *__restrict__ a, float4 *__restrict__ out, const uint2 *__restrict__ items, int n,
+                        flof_kd d, int nyb)
+{
+	const int q0 = (int)(blockIdx.x * FLOF_BLOCK + (threadIdx.x & ~31u));
+	if (q0 >= n) return;  // warp-uniform
+	const int lane = (int)(threadIdx.x & 31u), q = q0 + lane;
+	const bool valid = q < n;
+	const uint2 it = __ldg(items + (valid ? q : n - 1));
+	const unsigned mask = valid ? it.y : 0u;
+	unsigned id = it.x;
+	const unsigned id_l = __shfl_up_sync(0xffffffffu, it.x, 1), id_r = __shfl_down_sync(0xffffffffu, it.x, 1);
+	const int nzb = (d.nz + TZ - 1) / TZ;
+	const int x = (int)(id % (unsigned)d.nx);
+	id /= (unsigned)d.nx;
+	const int y0 = (int)(id % (unsigned)nyb) * FLOF_ETPY;
+	id /= (unsigned)nyb;
+	const int k0 = (int)(id % (unsigned)nzb) * TZ, t = (int)(id / (unsigned)nzb) + d.t0;
+	// the neighbouring lane holds the x-neighbour of the same rows exactly when the ids are consecutive (items have
+	// 1 <= x <= nx-2, so id - 1 / id + 1 stay inside the row)
+	const bool adj_l = lane > 0 && id_l + 1u == it.x;
+	const bool adj_r = lane < 31 && id_r == it.x + 1u && q + 1 < n;
+
+	p4 acc[TZ][FLOF_ETPY];
+#pragma unroll
+	for (int zo = 0; zo < TZ; ++zo)
+#pragma unroll
+		for (int oy = 0; oy < FLOF_ETPY; ++oy) acc[zo][oy] = p4_zero();
+	int roff[FLOF_ETPY + 2];
+#pragma unroll
+	for (int r = 0; r < FLOF_ETPY + 2; ++r) roff[r] = min(max(y0 - 1 + r, 0), d.ny - 1) * d.nx + x;
+	const int64_t sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
+#pragma unroll 1
+	for (int vt = t - 1; vt <= t + 1; ++vt) {
+#pragma unroll
+		for (int pz = 0; pz < TZ + 2; ++pz) {
+			const float4 *base = a + (sT * vt + sZ * min(max(k0 - 1 + pz, 0), d.nz - 1));
+			// row by row: the centre columns of all rows are requested first, each row's edge columns right before its adds
+			p4 C[FLOF_ETPY + 2];
+#pragma unroll
+			for (int r = 0; r < FLOF_ETPY + 2; ++r) C[r] = p4_load(base + roff[r]);
+#pragma unroll
+			for (int r = 0; r < FLOF_ETPY + 2; ++r) {
+				p4 L0 = p4_shfl_up(C[r]), L2 = p4_shfl_down(C[r]);
+				if (!adj_l) L0 = p4_load(base + roff[r] - 1);
+				if (!adj_r) L2 = p4_load(base + roff[r] + 1);
+#pragma unroll
+				for (int zo = 0; zo < TZ; ++zo) {
+					if (pz < zo || pz > zo + 2) continue;
+#pragma unroll
+					for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+						if (r < oy || r > oy + 2) continue;
+						acc4(acc[zo][oy], L0);
+						acc4(acc[zo][oy], C[r]);
+						acc4(acc[zo][oy], L2);
+					}
+				}
+			}
+		}
+	}
+	const double f = 1. / 81.0;
+#pragma unroll
+	for (int zo = 0; zo < TZ; ++zo) {
+		if (!((mask >> (zo * FLOF_ETPY)) & ((1u << FLOF_ETPY) - 1u))) continue;
+		float4 *o = out + (sT * t + sZ * (k0 + zo) + (int64_t)y0 * d.nx + x);
+#pragma unroll
+		for (int oy = 0; oy < FLOF_ETPY; ++oy) {
+			if (!((mask >> (zo * FLOF_ETPY + oy)) & 1u)) continue;
+			const float4 v = p4_unpack(acc[zo][oy]);
+			o[(int64_t)oy * d.nx] = make_float4((float)(v.x * f), (float)(v.y * f), (float)(v.z * f), (float)(v.w * f));
+		}
+	}
+}
+
 static int64_t flof_expol_zn_capacity(const flof_ctx *ctx, flof_dim4 d, int tz)
 {
 	int ta, tb;
@@ -509,7 +604,7 @@ static int flof_expol_zn_build(flof_ctx *ctx, const float *marker, flof_dim4 d, 
 	*n = (int)h[0];
 	return FLOF_OK;
 }
-static int flof_launch_expol_zn(flof_ctx *ctx, const float *a, float *out, const uint2 *items, int n, flof_dim4 d, int tz)
+static int flof_launch_expol_zn(flof_ctx *ctx, const float *a, float *out, const uint2 *items, int n, flof_dim4 d, int tz, int shfl)
 {
 	if (n <= 0) return FLOF_OK;
 	dim3 g;
@@ -518,6 +613,22 @@ static int flof_launch_expol_zn(flof_ctx *ctx, const float *a, float *out, const
 	const dim3 gi((unsigned)((n + FLOF_BLOCK - 1) / FLOF_BLOCK));
 #define FLOF_EZ_LAUNCH(TZ, MINB)                                                                                      \
 	FLOF_LAUNCH((k_cv_expol_items_zn<TZ, MINB>), gi, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)out, items, n, kd, nyb)
+#define FLOF_ES_LAUNCH(TZ, MINB)                                                                                      \
+	FLOF_LAUNCH((k_cv_expol_items_zs<TZ, MINB>), gi, FLOF_BLOCK, 0, (const float4 *)a, (float4 *)out, items, n, kd, nyb)
+	if (shfl) {
+		if (tz == 4) {
+			if (ctx->opt.expol_variant == 1)
+				FLOF_ES_LAUNCH(4, 1);
+			else
+				FLOF_ES_LAUNCH(4, 2);
+		} else {
+			if (ctx->opt.expol_variant == 1)
+				FLOF_ES_LAUNCH(2, 1);
+			else
+				FLOF_ES_LAUNCH(2, 2);
+		}
+		return FLOF_OK;
+	}
 	if (tz == 4) {
 		if (ctx->opt.expol_variant == 1)
 			FLOF_EZ_LAUNCH(4, 1);

@@ -34,7 +34,7 @@ def test_extrapolation_kernels_agree_bit_for_bit(env):
     assert 0.05 < float((m == 0).mean()) < 0.6           # the workload really is sparse-but-scattered
     out = {}
     default_mode = ctx.get_option("expol_mode")
-    for mode in (2, 1, 0, 3, 4):
+    for mode in (2, 1, 0, 3, 4, 5, 6):
         ctx.set_option("expol_mode", mode)
         dst.upload(start)
         ctx.cv_expol_blur4d(dst, mk, 7)
@@ -44,6 +44,7 @@ def test_extrapolation_kernels_agree_bit_for_bit(env):
     assert np.array_equal(out[0], out[2])
     assert np.array_equal(out[3], out[2])                 # 4y x 2z work-list items
     assert np.array_equal(out[4], out[2])                 # 4y x 4z work-list items
+    assert np.array_equal(out[5], out[2]) and np.array_equal(out[6], out[2])   # the same with lane shuffles
     # marked cells and the outer shell never change (ref knCvExpolBlur4d :613-626, bnd = 1)
     keep = (m != 0)
     keep[0], keep[-1], keep[:, 0], keep[:, -1] = True, True, True, True

@@ -140,7 +140,7 @@ def test_expol_work_list_paths_bitexact(gpu, dims):
         eq(gpu.cv_expol_blur4d(a, mark, sweeps), want)
         default_mode = gpu.ctx.get_option("expol_mode")
         try:
-            for mode in (1, 3, 4):                              # 4y / 4y x 2z / 4y x 4z items (odd nz, clamped planes, ragged lists)
+            for mode in (1, 3, 4, 5, 6):                              # 4y / 4y x 2z / 4y x 4z items (odd nz, clamped planes, ragged lists)
                 gpu.ctx.set_option("expol_mode", mode)
                 eq(gpu.cv_expol_blur4d(a, mark, sweeps), want)
         finally:
