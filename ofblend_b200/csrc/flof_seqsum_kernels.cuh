@@ -615,10 +615,49 @@ __device__ __forceinline__ void seq_walk(const seq_rec *st, int k0, int k1, doub
 __device__ __forceinline__ seq_rec seq_run_step(const seq_fn &f, int e)
 {
 	seq_rec o;
-	o.d0 = f.d0; o.d1 = f.d1; o.pad[0] = o.pad[1] = 0;
+	o.d0 = f.d0; o.d1 = f.d1; o.pad[0] = (int)f.q; o.pad[1] = 0;  // (pad[0]: the function's parities, for seq_precompose)
 	o.e = e > SEQ_E_WILD ? e + 1023 : 0;
 	o.q = e > SEQ_E_WILD ? 0x7ffu : 0u;
 	return o;
+}
+
+// Sharded level, ranks above 0: while the exact running sum of the lower ranks is still on its way, neighbouring run
+// steps of one binade are composed into one and identity steps dropped (in place; returns the new step count), so that
+// the part of the walk that sits in the rank-to-rank chain shrinks to the binade changes and raw products of this rank.
+__device__ __forceinline__ int seq_precompose(seq_rec *st, int N)
+{
+	int m = 0, e = 0;
+	bool have = false;
+	seq_fn f = seq_identity();
+	for (int k = 0; k < N; ++k) {
+		const seq_rec r = st[k];
+		if (r.q == 0x7ffu) {
+			const seq_fn g = { r.d0, r.d1, (unsigned)r.pad[0] };
+			if (have && e == r.e)
+				f = seq_compose(f, g);
+			else {
+				if (have) {
+					seq_rec o = seq_run_step(f, e - 1023);
+					st[m++] = o;
+				}
+				have = true;
+				e = r.e;
+				f = g;
+			}
+		} else if (r.d0 != 0. || r.d1 != 0.) {  // a raw product (identities add nothing: dropped)
+			if (have) {
+				seq_rec o = seq_run_step(f, e - 1023);
+				st[m++] = o;
+				have = false;
+			}
+			st[m++] = r;
+		}
+	}
+	if (have) {
+		seq_rec o = seq_run_step(f, e - 1023);
+		st[m++] = o;
+	}
+	return m;
 }
 
 template <int KIND>
@@ -787,6 +826,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 				atomicOr(&s_bad, 2u | 0x2000u);  // more raw leaves than the walk's side list takes
 			r.d0 = r.d1 = 0.;
 		}
+		r.pad[0] = (int)r.q;
 		r.q = r.e > SEQ_E_WILD ? 0x7ffu : 0u;  // (raw products carry d0 = d1 = the product)
 		r.e = r.e > SEQ_E_WILD ? r.e + 1023 : 0;
 		steps[s_jdst[lo] + j] = r;
@@ -797,6 +837,8 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	// ---- D: the sequential walk (one thread)
 	double S = 0.;
 	unsigned int cseq = 0;
+	int Nw = N;  // steps the walk takes
+	if (multi && pp.rank > 0 && in_smem && s_nraw == 0 && !s_bad && !(flags & 1u)) Nw = seq_precompose(s_st, N);
 	if (multi) {  // the running sum continues from the rank below (exact bits handed over through the mailboxes)
 		cseq = ++(*pp.chain_seq);
 		if (pp.rank > 0) {
@@ -823,7 +865,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		}
 		int k = 0;
 		for (int i = 0; i <= nraw; ++i) {
-			const int kend = i < nraw ? s_rawpos[i] : N;
+			const int kend = i < nraw ? s_rawpos[i] : Nw;
 			if (in_smem)
 				seq_walk(s_st, k, kend, S, wrong);
 			else
