@@ -471,9 +471,11 @@ def main():
             "cg_iters": m["cg_iters"],
             "final_error": m["errs"][-1] if m["errs"] else None,
             "gpu_launches": m["launches"],
-            # every rank uploads the (replicated) inputs and downloads the complete deformation: whole-job bytes
-            "e2e": {"value": m["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": cells * 24 * world, "d2h_bytes_per_step": cells * 16 * world,
-                    "bytes_per_rank": {"h2d": cells * 24, "d2h": cells * 16},
+            # every rank uploads its own t-slab of the inputs (all-gathered over NVLink) and downloads the complete
+            # deformation: whole-job bytes
+            "e2e": {"value": m["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": cells * 24 * (1 if res % world == 0 else world),
+                    "d2h_bytes_per_step": cells * 16 * world,
+                    "bytes_per_rank": {"h2d": cells * 24 // (world if res % world == 0 else 1), "d2h": cells * 16},
                     "api": "flof_optical_flow_multiscale4d_host (pinned host buffers)"},
             "clocks": m["clocks"],
             "roofline": roofline_of(m),

@@ -291,6 +291,11 @@ class Context:
                                                C.c_float(correction), int(bnd), C.byref(r)))
         return r.value
 
+    def calc_smoke_diff4d(self, i0, i1, correction=1., bnd=0):
+        r = C.c_float(0)
+        self._chk(self.lib.flof_calc_smoke_diff4d(self.h, i0.ptr, i1.ptr, i0.d4(), C.c_float(correction), int(bnd), C.byref(r)))
+        return r.value
+
     def optical_flow_multiscale4d(self, vel, i0, i1, params, want_trace=False):
         tr = MultiscaleTrace()
         err = C.c_float(0)
@@ -434,6 +439,9 @@ class HostAPI:
                 return r, o
             return r
         return self._run([i0, i1], f)
+
+    def calc_smoke_diff4d(self, i0, i1, correction=1., bnd=0):
+        return self._run([i0, i1], lambda a, b: self.ctx.calc_smoke_diff4d(a, b, correction, bnd))
 
     def optical_flow_multiscale4d(self, vel, i0, i1, want_trace=False, **kw):
         p = make_params(**kw)

@@ -319,6 +319,16 @@ int flof_allgather_slabs(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes)
 	return FLOF_OK;
 }
 
+// in-place all-gather of equal byte ranges: this rank's part sits at buf + off (off = rank * n)
+int flof_allgather_bytes(flof_ctx *ctx, void *buf, size_t off, size_t n)
+{
+	if (!ctx->comm || ctx->nranks <= 1) return FLOF_OK;
+	const int pi = flof_prof_pre(ctx, "nccl_allgather_inputs");
+	FLOF_NCCL(ncclAllGather((char *)buf + off, buf, n, ncclChar, (ncclComm_t)ctx->comm, ctx->stream));
+	flof_prof_post(ctx, pi);
+	return FLOF_OK;
+}
+
 static int flof_allreduce_scalar(flof_ctx *ctx, void *dev, int n, int kind)
 {
 	if (!ctx->comm || ctx->nranks <= 1) return FLOF_OK;

@@ -152,6 +152,7 @@ static inline bool flof_sharded(const flof_ctx *ctx, int nt) { return ctx->sh.ac
 int flof_halo_exchange(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes, int h);
 int flof_p2p_ensure(flof_ctx *ctx, size_t need);  // collective: maps the peer mailboxes (halo buffers >= need bytes)
 int flof_allgather_slabs(flof_ctx *ctx, void *grid, int nt, size_t slice_bytes);
+int flof_allgather_bytes(flof_ctx *ctx, void *buf, size_t off, size_t n);
 int flof_allreduce_f64_sum(flof_ctx *ctx, double *dev, int n);
 int flof_allreduce_f32_max(flof_ctx *ctx, float *dev, int n);
 int flof_allreduce_f32_min(flof_ctx *ctx, float *dev, int n);

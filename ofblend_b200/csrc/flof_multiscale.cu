@@ -376,9 +376,23 @@ extern "C" int flof_optical_flow_multiscale4d_host(flof_ctx *ctx, float *vel_h, 
 	MS_RET(vel.alloc(vb, false));
 	MS_RET(i0.alloc(rb, false));
 	MS_RET(i1.alloc(rb, false));
-	MS_RET(flof_memcpy_h2d(ctx, i0.p, i0_h, rb));
-	MS_RET(flof_memcpy_h2d(ctx, i1.p, i1_h, rb));
-	MS_RET(flof_memcpy_h2d(ctx, vel.p, vel_h, vb));
+	if (ctx->comm && ctx->nranks > 1 && d.nt % ctx->nranks == 0) {
+		// N ranks: every rank uploads only its own t-slab of the (replicated) host buffers -- 1/N of the bytes over PCIe --
+		// and the slabs are all-gathered over NVLink (NCCL, in place)
+		int ta, tb;
+		flof_slab_range(d.nt, ctx->nranks, ctx->rank, &ta, &tb);
+		const size_t s1 = sizeof(float) * (size_t)d.nx * d.ny * d.nz, o1 = s1 * (size_t)ta, n1 = s1 * (size_t)(tb - ta);
+		MS_RET(flof_memcpy_h2d(ctx, (char *)i0.p + o1, (const char *)i0_h + o1, n1));
+		MS_RET(flof_memcpy_h2d(ctx, (char *)i1.p + o1, (const char *)i1_h + o1, n1));
+		MS_RET(flof_memcpy_h2d(ctx, (char *)vel.p + 4 * o1, (const char *)vel_h + 4 * o1, 4 * n1));
+		MS_RET(flof_allgather_bytes(ctx, i0.p, o1, n1));
+		MS_RET(flof_allgather_bytes(ctx, i1.p, o1, n1));
+		MS_RET(flof_allgather_bytes(ctx, vel.p, 4 * o1, 4 * n1));
+	} else {
+		MS_RET(flof_memcpy_h2d(ctx, i0.p, i0_h, rb));
+		MS_RET(flof_memcpy_h2d(ctx, i1.p, i1_h, rb));
+		MS_RET(flof_memcpy_h2d(ctx, vel.p, vel_h, vb));
+	}
 	MS_RET(flof_optical_flow_multiscale4d(ctx, vel.f(), i0.f(), i1.f(), d, p, tr, err_out));
 	MS_RET(flof_memcpy_d2h(ctx, vel_h, vel.p, vb));
 	return FLOF_OK;

@@ -171,6 +171,10 @@ struct GridAny {
 	size_t bytes() const { return (size_t)cells * elem * 4; }
 	void alloc() { CK(flof_malloc(ctx(), &ptr, bytes()), "Grid"); }
 	float *f() const { return (float *)ptr; }
+	void sameRes(const GridAny &o, const char *fn) const  // same cell count / dims, element type may differ
+	{
+		if (o.cells != cells) errMsg(std::string(fn) + ": different grid resolutions");
+	}
 	void sameSize(const GridAny &o, const char *fn) const
 	{
 		if (o.cells != cells || o.elem != elem) errMsg(std::string(fn) + ": different grid resolutions / types");
@@ -178,9 +182,9 @@ struct GridAny {
 	// element-wise ops shared by 3D and 4D grids (ref grid4d.h:338-372 / grid.h:220-252)
 	void clear() { CK(flof_memset0(ctx(), ptr, bytes()), "clear"); }
 	void copyFrom(const GridAny &a) { sameSize(a, "copyFrom"); CK(flof_memcpy_d2d(ctx(), ptr, a.ptr, bytes()), "copyFrom"); }
-	void add(const GridAny &a) { sameSize(a, "add"); CK(flof_grid_binary(ctx(), f(), a.f(), cells, elem, FLOF_OP_ADD), "add"); }
-	void sub(const GridAny &a) { sameSize(a, "sub"); CK(flof_grid_binary(ctx(), f(), a.f(), cells, elem, FLOF_OP_SUB), "sub"); }
-	void mult(const GridAny &a) { sameSize(a, "mult"); CK(flof_grid_binary(ctx(), f(), a.f(), cells, elem, FLOF_OP_MULT), "mult"); }
+	void add(const GridAny &a) { needFloat("add"); sameSize(a, "add"); CK(flof_grid_binary(ctx(), f(), a.f(), cells, elem, FLOF_OP_ADD), "add"); }
+	void sub(const GridAny &a) { needFloat("sub"); sameSize(a, "sub"); CK(flof_grid_binary(ctx(), f(), a.f(), cells, elem, FLOF_OP_SUB), "sub"); }
+	void mult(const GridAny &a) { needFloat("mult"); sameSize(a, "mult"); CK(flof_grid_binary(ctx(), f(), a.f(), cells, elem, FLOF_OP_MULT), "mult"); }
 	void factor(const py::handle &s, float o[4]) const
 	{
 		if (kind == K_VEC4) v4arr(toV4(s), o);
@@ -864,7 +868,8 @@ PYBIND11_MODULE(manta, m)
 		      if (vel.parent->dt != 1.0f) errMsg("Invalid, only dt 1 for now!");
 		      if (blurType.v != 1) errMsg("NYI");
 		      if (level.v != 0) errMsg(std::string(fn) + ": level must be 0 when called from a scene");
-		      (void)optGrid<Grid4>(rhsT, fn); (void)orderTime; (void)orderSpace;
+		      if (optGrid<Grid4>(rhsT, fn)) errMsg(std::string(fn) + ": rhsT is not filled by the multi-scale driver on the B200 path (use opticalFlow4d)");
+		      (void)orderTime; (void)orderSpace;
 		      flof_multiscale_params p;
 		      flof_multiscale_defaults(&p);
 		      p.wSmooth = wSmooth; p.wEnergy = wEnergy; p.postVelBlur = postVelBlur; p.cgAccuracy = cgAccuracy; p.cfl = cfl;
@@ -891,8 +896,10 @@ PYBIND11_MODULE(manta, m)
 	         PInt blurType, float resetBndWidth) {
 		      const char *fn = "opticalFlow4d";
 		      requireKind(vel, K_VEC4, fn, "vel"); requireKind(i0, K_REAL, fn, "i0"); requireKind(i1, K_REAL, fn, "i1");
+		      vel.sameRes(i0, fn); vel.sameRes(i1, fn);
 		      if (blurType.v != 1) errMsg("NYI");
 		      Grid4 *r = optGrid<Grid4>(rhsT, fn);
+		      if (r) { requireKind(*r, K_REAL, fn, "rhsT"); vel.sameRes(*r, fn); }
 		      int it = 0; float res = 0.f;
 		      CK(flof_optical_flow4d(ctx(), vel.f(), i0.f(), i1.f(), r ? r->f() : nullptr, vel.d, wSmooth, wEnergy, postVelBlur, cgAccuracy,
 		                             resetBndWidth, &it, &res), fn);
@@ -905,7 +912,11 @@ PYBIND11_MODULE(manta, m)
 	m.def("corrVelsOf4d",
 	      [](Grid4 &dst, Grid4 &vel, Grid4 &phiOrg, Grid4 &phiCurr, Grid4 &phiTarget, float threshPhi, float threshNorm, float postVelBlur,
 	         float resetBndWidth, PInt maxIter) {
-		      (void)phiCurr; (void)threshNorm;
+		      (void)threshNorm;
+		      const char *fn = "corrVelsOf4d";
+		      requireKind(dst, K_VEC4, fn, "dst"); requireKind(vel, K_VEC4, fn, "vel"); requireKind(phiOrg, K_REAL, fn, "phiOrg");
+		      requireKind(phiCurr, K_REAL, fn, "phiCurr"); requireKind(phiTarget, K_REAL, fn, "phiTarget");
+		      vel.sameRes(dst, fn); vel.sameRes(phiOrg, fn); vel.sameRes(phiTarget, fn);
 		      CK(flof_corr_vels_of4d(ctx(), dst.f(), vel.f(), phiOrg.f(), phiTarget.f(), vel.d, threshPhi, postVelBlur, resetBndWidth, maxIter.v),
 		         "corrVelsOf4d");
 	      },
@@ -916,6 +927,8 @@ PYBIND11_MODULE(manta, m)
 	m.def("calcLsDiff4d",
 	      [](Grid4 &i0, Grid4 &i1, const py::object &out, float correction, PInt bnd) {
 		      Grid4 *o = optGrid<Grid4>(out, "calcLsDiff4d");
+		      requireKind(i0, K_REAL, "calcLsDiff4d", "i0"); requireKind(i1, K_REAL, "calcLsDiff4d", "i1"); i0.sameSize(i1, "calcLsDiff4d");
+		      if (o) { requireKind(*o, K_REAL, "calcLsDiff4d", "out"); i0.sameSize(*o, "calcLsDiff4d"); }
 		      float r = 0.f;
 		      CK(flof_calc_ls_diff4d(ctx(), i0.f(), i1.f(), o ? o->f() : nullptr, i0.d, correction, bnd.v, &r), "calcLsDiff4d");
 		      return r;
@@ -923,6 +936,7 @@ PYBIND11_MODULE(manta, m)
 	      py::arg("i0"), py::arg("i1"), py::arg("out") = py::none(), py::arg("correction") = 1.f, py::arg("bnd") = PInt{ 0 });
 	m.def("calcSmokeDiff4d",
 	      [](Grid4 &i0, Grid4 &i1, const py::object &, float correction, PInt bnd) {
+		      requireKind(i0, K_REAL, "calcSmokeDiff4d", "i0"); requireKind(i1, K_REAL, "calcSmokeDiff4d", "i1"); i0.sameSize(i1, "calcSmokeDiff4d");
 		      float r = 0.f;
 		      CK(flof_calc_smoke_diff4d(ctx(), i0.f(), i1.f(), i0.d, correction, bnd.v, &r), "calcSmokeDiff4d");
 		      return r;
@@ -934,6 +948,7 @@ PYBIND11_MODULE(manta, m)
 	      [](Grid4 &vel, Grid4 &grid, float dtFac) {
 		      requireKind(vel, K_VEC4, "advect4d", "vel");
 		      if (!(grid.kind == K_REAL || grid.kind == K_VEC4)) errMsg("AdvectSemiLagrange4d: Grid Type is not supported (only Real, Vec4 on B200)");
+		      vel.sameRes(grid, "advect4d");
 		      CK(flof_advect4d(ctx(), vel.f(), grid.f(), grid.d, grid.elem, vel.parent->dt * dtFac), "advect4d");
 	      },
 	      py::arg("vel"), py::arg("grid"), py::arg("dtFac") = 1.f);
@@ -944,9 +959,12 @@ PYBIND11_MODULE(manta, m)
 		      CK(flof_extrap4d_ls_simple(ctx(), phi.f(), phi.d, distance.v, inside ? 1 : 0, nullptr), "extrap4dLsSimple");
 	      }, py::arg("phi"), py::arg("distance") = PInt{ 4 }, py::arg("inside") = false);
 	m.def("extrapolateVec4Simple", [](Grid4 &vel, Grid4 &phi, PInt distance) {
+		      requireKind(vel, K_VEC4, "extrapolateVec4Simple", "vel"); requireKind(phi, K_REAL, "extrapolateVec4Simple", "phi");
+		      vel.sameRes(phi, "extrapolateVec4Simple");
 		      CK(flof_extrapolate_vec4_simple(ctx(), vel.f(), phi.f(), phi.d, distance.v), "extrapolateVec4Simple");
 	      }, py::arg("vel"), py::arg("phi"), py::arg("distance"));
 	m.def("repeatFrame4d", [](Grid4 &phi, float srct, float range, PInt bnd) {
+		      requireKind(phi, K_REAL, "repeatFrame4d", "phi");
 		      CK(flof_repeat_frame4d(ctx(), phi.f(), phi.d, srct, range, bnd.v), "repeatFrame4d");
 	      }, py::arg("phi"), py::arg("srct"), py::arg("range") = 0.f, py::arg("bnd") = PInt{ 0 });
 
@@ -978,8 +996,8 @@ PYBIND11_MODULE(manta, m)
 		      if (src.d.nx != dst.d.nx || src.d.ny != dst.d.ny || src.d.nz != dst.d.nz) errMsg("placeGrid3d: 3D size of src must match dst");
 		      CK(flof_place_grid3d(ctx(), src.f(), dst.f(), dst.d, dstt.v), "placeGrid3d");
 	      }, py::arg("src"), py::arg("dst"), py::arg("dstt"));
-	m.def("getComp4d", [](Grid4 &src, Grid4 &dst, PInt c) { CK(flof_get_comp4d(ctx(), src.f(), dst.f(), src.cells, c.v), "getComp4d"); }, py::arg("src"), py::arg("dst"), py::arg("c"));
-	m.def("setComp4d", [](Grid4 &src, Grid4 &dst, PInt c) { CK(flof_set_comp4d(ctx(), src.f(), dst.f(), src.cells, c.v), "setComp4d"); }, py::arg("src"), py::arg("dst"), py::arg("c"));
+	m.def("getComp4d", [](Grid4 &src, Grid4 &dst, PInt c) { requireKind(src, K_VEC4, "getComp4d", "src"); requireKind(dst, K_REAL, "getComp4d", "dst"); src.sameRes(dst, "getComp4d"); CK(flof_get_comp4d(ctx(), src.f(), dst.f(), src.cells, c.v), "getComp4d"); }, py::arg("src"), py::arg("dst"), py::arg("c"));
+	m.def("setComp4d", [](Grid4 &src, Grid4 &dst, PInt c) { requireKind(src, K_REAL, "setComp4d", "src"); requireKind(dst, K_VEC4, "setComp4d", "dst"); src.sameRes(dst, "setComp4d"); CK(flof_set_comp4d(ctx(), src.f(), dst.f(), src.cells, c.v), "setComp4d"); }, py::arg("src"), py::arg("dst"), py::arg("c"));
 	m.def("setRegion4d", [](Grid4 &dst, const py::object &start, const py::object &end, float value) {
 		      float s[4], e[4]; v4arr(toV4(start), s); v4arr(toV4(end), e);
 		      const float v[4] = { value, value, value, value };
@@ -1011,7 +1029,7 @@ PYBIND11_MODULE(manta, m)
 	      }, py::arg("phi1"), py::arg("phi2"), py::arg("phiDiff"), py::arg("vel1"), py::arg("vel2"), py::arg("velt1"), py::arg("velt2"),
 	      py::arg("velDiff"), py::arg("bnd"));
 	m.def("debugGridAvg4d", [](Grid4 &phi, PInt brd) { float o = 0.f; CK(flof_debug_grid_avg4d(ctx(), phi.f(), phi.d, brd.v, &o), "debugGridAvg4d"); return o; }, py::arg("phi"), py::arg("brd") = PInt{ 0 });
-	m.def("initVecFromScalar", [](Grid4 &source, Grid4 &target) { CK(flof_init_vec_from_scalar(ctx(), source.f(), target.f(), source.cells), "initVecFromScalar"); }, py::arg("source"), py::arg("target"));
+	m.def("initVecFromScalar", [](Grid4 &source, Grid4 &target) { requireKind(source, K_REAL, "initVecFromScalar", "source"); requireKind(target, K_VEC4, "initVecFromScalar", "target"); source.sameRes(target, "initVecFromScalar"); CK(flof_init_vec_from_scalar(ctx(), source.f(), target.f(), source.cells), "initVecFromScalar"); }, py::arg("source"), py::arg("target"));
 	m.def("initTestCheckerboard", [](Grid4 &val, const py::object &vec, PInt brd) {
 		      Grid4 *v = optGrid<Grid4>(vec, "initTestCheckerboard");
 		      CK(flof_init_test_checkerboard(ctx(), val.f(), v ? v->f() : nullptr, val.d, brd.v), "initTestCheckerboard");

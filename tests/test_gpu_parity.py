@@ -156,6 +156,36 @@ def test_calc_ls_diff(gpu):
         eq(oa, ob)
 
 
+def test_calc_smoke_diff(gpu):
+    """calcSmokeDiff4d (ref optflow4d.cpp:2140-2168): sum of float(|i0 - i1| * correction) over the cells inside bnd,
+    accumulated in double, * 1e6 / cells.  The kernel sums in a different (deterministic) order: last bits of the fp64
+    sum only."""
+    i0, i1 = sdf_pair(D)
+    for bnd, corr in ((0, 1.), (2, 200.)):
+        sl = (slice(bnd, SH[0] - bnd), slice(bnd, SH[1] - bnd), slice(bnd, SH[2] - bnd), slice(bnd, SH[3] - bnd))
+        d = (np.abs(i0[sl] - i1[sl]) * np.float32(corr)).astype(np.float32)
+        want = d.astype(np.float64).sum() * 1e6 / d.size
+        got = gpu.calc_smoke_diff4d(i0, i1, corr, bnd)
+        assert abs(got - want) <= 2e-6 * abs(want), (got, want)
+
+
+def test_host_buffer_entry_equals_resident_call(gpu):
+    """flof_optical_flow_multiscale4d_host (the end-to-end plugin call: host buffers in and out) delivers the bits of the
+    resident call."""
+    from ofblend_b200 import capi
+    d = (24, 24, 24, 20)
+    i0, i1 = sdf_pair(d, seed=3)
+    v0 = np.zeros((d[3], d[2], d[1], d[0], 4), np.float32)
+    kw = dict(wSmooth=1e-3, wEnergy=1e-4, postVelBlur=4., cgAccuracy=1e-2, cfl=999., resetBndWidth=0.1,
+              multiStep=3, minGridSize=20, doFinalProject=True)
+    a, it_a, err_a = gpu.optical_flow_multiscale4d(v0, i0, i1, want_trace=True, **kw)
+    vh = np.ascontiguousarray(v0.copy())
+    err_b, tr = gpu.ctx.optical_flow_multiscale4d_host(vh, np.ascontiguousarray(i0), np.ascontiguousarray(i1), capi.make_params(**kw))
+    assert list(tr.cg_iters[:tr.n_solves]) == it_a
+    assert np.array_equal(vh, a)
+    assert err_b == err_a[-1]
+
+
 def test_extrapolation_marker_bitexact(gpu):
     i0, _ = sdf_pair(D)
     phi = port.set_bound4d(i0 / np.float32(-0.005), 0.1, 1)
