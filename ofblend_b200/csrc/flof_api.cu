@@ -76,6 +76,7 @@ int flof_ctx_create(flof_ctx **out, int device)
 	c->opt.expol_mode = getenv("FLOF_EXPOL_MODE") ? atoi(getenv("FLOF_EXPOL_MODE")) : -1;  // -1: by grid size (flof_blur.cu)
 	c->opt.expol_variant = getenv("FLOF_EXPOL_VARIANT") ? atoi(getenv("FLOF_EXPOL_VARIANT")) : 0;
 	c->opt.apply_variant = getenv("FLOF_APPLY_VARIANT") ? atoi(getenv("FLOF_APPLY_VARIANT")) : 11;
+	c->opt.apply_zchunk = getenv("FLOF_APPLY_ZCHUNK") ? atoi(getenv("FLOF_APPLY_ZCHUNK")) : -1;
 	c->opt.dot_mode = getenv("FLOF_DOT_MODE") ? atoi(getenv("FLOF_DOT_MODE")) : 1;
 	c->opt.no_p2p = getenv("FLOF_NO_P2P") ? 1 : 0;
 	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -122,6 +123,7 @@ int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value)
 	else if (!strcmp(name, "apply_variant")) ctx->opt.apply_variant = value;
 	else if (!strcmp(name, "dot_mode")) ctx->opt.dot_mode = value;
 	else if (!strcmp(name, "no_p2p")) ctx->opt.no_p2p = value;
+	else if (!strcmp(name, "apply_zchunk")) ctx->opt.apply_zchunk = value;
 	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_set_option: unknown option '%s'", name);
 	return FLOF_OK;
 }
@@ -133,6 +135,7 @@ int flof_ctx_get_option(flof_ctx *ctx, const char *name, int *value)
 	else if (!strcmp(name, "apply_variant")) *value = ctx->opt.apply_variant;
 	else if (!strcmp(name, "dot_mode")) *value = ctx->opt.dot_mode;
 	else if (!strcmp(name, "no_p2p")) *value = ctx->opt.no_p2p;
+	else if (!strcmp(name, "apply_zchunk")) *value = ctx->opt.apply_zchunk;
 	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_get_option: unknown option '%s'", name);
 	return FLOF_OK;
 }

@@ -109,6 +109,7 @@ struct flof_ctx {
 		int expol_variant;  // register budget / unrolling variant of the chosen extrapolation kernel
 		int apply_variant;  // CG apply: 11 (default) = streaming hints + 6 CTAs/SM (40 registers, no spills); 7 = 8 CTAs/SM; 0, 1, 3, 5, 9, 10 other occupancy / unrolling points
 		int no_p2p;         // 1: keep NCCL for halos and CG scalars (no NVLink peer mailboxes; tree-order dot products)
+		int apply_zchunk;   // CG apply: z-planes per chunk of the leaf order (-1 = by grid size, 0 = plain index order)
 		int dot_mode;       // CG dot products: 1 (default) = the reference's sequential summation order, bit for bit
 		                    // (flof_seqsum); 0 = tree reductions (faster, last bits of the fp64 sums differ)
 	} opt;
