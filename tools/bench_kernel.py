@@ -30,6 +30,11 @@ def main():
     ctx.project_cells(dst, vel, i0, i1, mk, 4., 40)                       # realistic marker / projected field
 
     def run(name):
+        if "@" in name:
+            name, v = name.split("@")          # "expol@7.1": expol_mode 7, expol_variant 1
+            mode, _, var = v.partition(".")
+            ctx.set_option("expol_mode", int(mode))
+            ctx.set_option("expol_variant", int(var or 0))
         if name == "expol":
             ctx.cv_expol_blur4d(dst, mk, 8)
         elif name == "gauss":
