@@ -313,6 +313,24 @@ int flof_load_advect_time_slice_unopt(flof_ctx *ctx, const float *defo_vec4, flo
                                       const float defoOffset[4], const float defoScale[4], const float defoFactor[4],
                                       const float overrideSize[4], float overrideTimeOff, float defoAniFac, int zeroVel,
                                       float *dbgVel3, float *dbgVelT);
+/* ---- 3D instantiations of the optical-flow templates (scenes/opticalFlowSimple3d.py) ----------------
+ * Grids are nx*ny*nz arrays, x fastest; velocities are Vec3 AoS (3 floats per cell) like the reference's Grid<Vec3>.
+ * 2D grids (nz == 1) are not built. */
+/* ref: opticalFlowMultiscale3d optflow4d.cpp:1175-1188 (template :936-1173 with Grid<Real> / Grid<Vec3>).  Synchronises. */
+int flof_optical_flow_multiscale3d(flof_ctx *ctx, float *vel_vec3, const float *i0, const float *i1, flof_dim3 d,
+                                   const flof_multiscale_params *p, flof_multiscale_trace *tr, float *err_out);
+/* ref: corrVelsOf3d :803-812 (corrVelsOfTempl :737-802; phiCurr and threshNorm are unused there).  Synchronises. */
+int flof_corr_vels_of3d(flof_ctx *ctx, float *dst_vec3, float *vel_vec3, const float *phiOrg, const float *phiTarget,
+                        flof_dim3 d, float threshPhi, float postVelBlur, float resetBndWidth, int maxIter);
+/* ref: advectSemiLagrangeCfl :863-872 (centred velocities, CFL sub-steps :841-853; flags / order / orderSpace are
+ * unused there); elem 1 = Grid<Real> payload, 3 = Grid<Vec3>.  advectCent3d :836 = the same with one step (cfl above
+ * max|vel|).  Synchronises. */
+int flof_advect_semi_lagrange_cfl3d(flof_ctx *ctx, float cfl, const float *vel_vec3, float *grid, int elem, flof_dim3 d,
+                                    float velFactor);
+/* ref: calcLsDiff3d :928-933 (calcLsDiffTempl :895-927).  Synchronises. */
+int flof_calc_ls_diff3d(flof_ctx *ctx, const float *i0, const float *i1, float *out_or_null, flof_dim3 d,
+                        float correction, int bnd, float *result);
+
 /* ref: simpleBlurSpecial test.cpp:127 */
 int flof_simple_blur_special(flof_ctx *ctx, float *a, flof_dim3 d, int iter, float thresh,
                              int bord);

@@ -313,6 +313,30 @@ class Context:
             i1_h.ctypes.data_as(C.c_void_p), d, C.byref(params), C.byref(tr), C.byref(err)))
         return err.value, tr
 
+    # ---- 3D instantiations: grids created with ctx.grid3(dims3, elem), velocities elem = 3 (Vec3 AoS)
+    def optical_flow_multiscale3d(self, vel, i0, i1, params, want_trace=False):
+        tr = MultiscaleTrace()
+        err = C.c_float(0)
+        self._chk(self.lib.flof_optical_flow_multiscale3d(self.h, vel.ptr, i0.ptr, i1.ptr, i0.d3(), C.byref(params),
+                                                          C.byref(tr), C.byref(err)))
+        return (err.value, tr) if want_trace else err.value
+
+    def corr_vels_of3d(self, dst, vel, phi_org, phi_target, thresh_phi=1e10, post_vel_blur=0., reset_bnd_width=-1.,
+                       max_iter=100):
+        self._chk(self.lib.flof_corr_vels_of3d(self.h, dst.ptr, vel.ptr, phi_org.ptr, phi_target.ptr, phi_org.d3(),
+                                               C.c_float(thresh_phi), C.c_float(post_vel_blur), C.c_float(reset_bnd_width),
+                                               int(max_iter)))
+
+    def advect_semi_lagrange_cfl3d(self, cfl, vel, grid, vel_factor=1.):
+        self._chk(self.lib.flof_advect_semi_lagrange_cfl3d(self.h, C.c_float(cfl), vel.ptr, grid.ptr, int(grid.elem),
+                                                           vel.d3(), C.c_float(vel_factor)))
+
+    def calc_ls_diff3d(self, i0, i1, out=None, correction=1., bnd=0):
+        r = C.c_float(0)
+        self._chk(self.lib.flof_calc_ls_diff3d(self.h, i0.ptr, i1.ptr, out.ptr if out else None, i0.d3(),
+                                               C.c_float(correction), int(bnd), C.byref(r)))
+        return r.value
+
     def repeat_frame4d(self, phi, srct, rng=0., bnd=0):
         self._chk(self.lib.flof_repeat_frame4d(self.h, phi.ptr, phi.d4(), C.c_float(srct), C.c_float(rng), int(bnd)))
 
@@ -453,6 +477,52 @@ class HostAPI:
                 return out, list(tr.cg_iters[:tr.n_solves]), [float(x) for x in tr.errs[:tr.n_errs]]
             return out
         return self._run([vel, i0, i1], f)
+
+    # ---- 3D instantiations: numpy layout [z, y, x(, 3)]
+    def _g3(self, a):
+        a = np.ascontiguousarray(a, np.float32)
+        return DeviceGrid(self.ctx, (a.shape[2], a.shape[1], a.shape[0]), 3 if a.ndim == 4 else 1).upload(a)
+
+    def optical_flow_multiscale3d(self, vel, i0, i1, want_trace=False, **kw):
+        p = make_params(**kw)
+        gs = [self._g3(vel), self._g3(i0), self._g3(i1)]
+        try:
+            err, tr = self.ctx.optical_flow_multiscale3d(gs[0], gs[1], gs[2], p, want_trace=True)
+            out = gs[0].download()
+            if want_trace:
+                return out, list(tr.cg_iters[:tr.n_solves]), [float(x) for x in tr.errs[:tr.n_errs]]
+            return out
+        finally:
+            for g in gs:
+                g.free()
+
+    def corr_vels_of3d(self, dst, vel, phiOrg, phiTarget, threshPhi=1e10, postVelBlur=0., resetBndWidth=-1., maxIter=100):
+        gs = [self._g3(dst), self._g3(vel), self._g3(phiOrg), self._g3(phiTarget)]
+        try:
+            self.ctx.corr_vels_of3d(gs[0], gs[1], gs[2], gs[3], threshPhi, postVelBlur, resetBndWidth, maxIter)
+            return gs[0].download(), gs[1].download()
+        finally:
+            for g in gs:
+                g.free()
+
+    def advect_semi_lagrange_cfl3d(self, cfl, vel, grid, velFactor=1.):
+        gs = [self._g3(vel), self._g3(grid)]
+        try:
+            self.ctx.advect_semi_lagrange_cfl3d(cfl, gs[0], gs[1], velFactor)
+            return gs[1].download()
+        finally:
+            for g in gs:
+                g.free()
+
+    def calc_ls_diff3d(self, i0, i1, correction=1., bnd=0, want_out=False):
+        gs = [self._g3(i0), self._g3(i1)]
+        out = DeviceGrid(self.ctx, gs[0].dims, 1) if want_out else None
+        try:
+            r = self.ctx.calc_ls_diff3d(gs[0], gs[1], out, correction, bnd)
+            return (r, out.download()) if want_out else r
+        finally:
+            for g in gs + ([out] if out else []):
+                g.free()
 
     def extrap4d_ls_simple(self, phi, distance=4, inside=False, want_marker=False):
         def f(p):

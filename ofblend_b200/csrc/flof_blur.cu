@@ -42,7 +42,10 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 {
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t)) return;
-	if (!flof_in_bounds(d, i, j, k, t, 1)) return;
+	// KERNEL(fourd, bnd = 1): a one-slice grid is not 4D in the reference (kernel.h:62-68), t is unbounded there --
+	// the 3D instantiation gaussianBlurGeneric<Grid<Vec3>> runs through this kernel with d.nt == 1
+	if (d.nt == 1 ? !(i >= 1 && j >= 1 && k >= 1 && i < d.nx - 1 && j < d.ny - 1 && k < d.nz - 1) : !flof_in_bounds(d, i, j, k, t, 1))
+		return;
 	T val = blur_zero<T>();
 	float weight = 0.f;
 	const int x0 = max(i - S, 0), x1 = min(i + S, d.nx - 1);

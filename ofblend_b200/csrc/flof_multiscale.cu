@@ -17,6 +17,16 @@ int flof_optical_flow4d_ex(flof_ctx *ctx, float *vel, const float *i0, const flo
                             float wSmooth, float wEnergy, float postVelBlur, float cgAccuracy,
                             float resetBndWidth, int vel_is_zero, int *cgIters, float *cgRes);
 
+// 3D operators (flof_dim3.cu): padded float4 velocities, d.nt == 1
+int flof3_interpol_grid(flof_ctx *ctx, float *dst, flof_dim4 td, const float *src, flof_dim4 sd, int elem);
+int flof3_advect_cfl(flof_ctx *ctx, float cfl, const float *vel, float *grid, flof_dim4 d, int elem, float velFactor);
+int flof3_set_bound_neumann(flof_ctx *ctx, float *grid, flof_dim4 d, int elem, int w);
+int flof3_optical_flow(flof_ctx *ctx, float *vel, const float *i0, const float *i1, float *rhsT, flof_dim4 d, float wSmooth,
+                       float wEnergy, float postVelBlur, float cgAccuracy, float resetBndWidth, int vel_is_zero, int *cgIters,
+                       float *cgRes);
+int flof3_corr_vels(flof_ctx *ctx, float *dst, float *vel, const float *phiOrg, const float *phiTarget, flof_dim4 d,
+                    float threshPhi, float postVelBlur, float resetBndWidth, int maxIter);
+
 // ------------------------------------------------------------------ error metric ----------
 // SMOKE = false: sign-mismatch masked, clamped |diff| (ref :902-912); SMOKE = true: plain |diff|.
 // the metric kernels are launched over a 1-D grid of row-blocks; each block walks its rows in
@@ -31,7 +41,10 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	for (int row = row0 + blockIdx.x; row < row1; row += gridDim.x) {  // one row = nx cells
 		const int j = row % d.ny, k = (row / d.ny) % d.nz, t = row / (d.ny * d.nz);
 		for (int i = threadIdx.x; i < d.nx; i += blockDim.x) {
-			if (!flof_in_bounds(d, i, j, k, t, bnd)) continue;
+			// FOR_IJKT_BND kernel.h:62-68: t is bounded only on a 4D grid (sizeT > 1), z only on a 3D one
+			if (i < bnd || j < bnd || i >= d.nx - bnd || j >= d.ny - bnd) continue;
+			if (d.nz > 1 && (k < bnd || k >= d.nz - bnd)) continue;
+			if (d.nt > 1 && (t < bnd || t >= d.nt - bnd)) continue;
 			const int64_t c = flof_idx(d, i, j, k, t);
 			const float a = __ldg(i0 + c), b = __ldg(i1 + c);
 			if (SMOKE) {
@@ -74,7 +87,7 @@ static int ls_diff(flof_ctx *ctx, const float *i0, const float *i1, float *out, 
 	FLOF_CK(cudaMemcpyAsync(h, &ctx->red->out_d[2], sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	FLOF_CK(cudaStreamSynchronize(ctx->stream));
 	double accu = h[0];
-	const int sx = d.nx - 2 * bnd, sy = d.ny - 2 * bnd, sz = d.nz - 2 * bnd, st = d.nt - 2 * bnd;
+	const int sx = d.nx - 2 * bnd, sy = d.ny - 2 * bnd, sz = d.nz > 1 ? d.nz - 2 * bnd : d.nz, st = d.nt > 1 ? d.nt - 2 * bnd : d.nt;  // ref :915-922
 	accu *= 1000.;
 	if (d.nt > 1) accu *= 1000.;
 	accu *= 1. / (double)(sx * sy * sz * st);
@@ -142,10 +155,39 @@ void tr_err(flof_multiscale_trace *tr, float e)
 		if (r__ != FLOF_OK) return r__;    \
 	} while (0)
 
+// The driver serves the 4D template instantiation and the 3D one (Grid<Real> / Grid<Vec3>, ref :1175-1188): a level with
+// d.nt == 1 is a 3D grid (velocities padded to float4) and every operator below dispatches to its 3D form (flof_dim3.cu).
+inline bool is3(flof_dim4 d) { return d.nt == 1; }
 // complete: `grid` is valid on all slices (fresh copy of an input) -> no all-gather on a sharded level
 int advect_cfl(flof_ctx *ctx, float cfl, const float *vel, float *grid, flof_dim4 d, int elem, int complete)
 {
+	if (is3(d)) return flof3_advect_cfl(ctx, cfl, vel, grid, d, elem, 1.f);
 	return flof_advect_cfl4d_ex(ctx, cfl, vel, grid, d, elem, 1.f, complete);
+}
+int resample(flof_ctx *ctx, float *dst, flof_dim4 td, const float *src, flof_dim4 sd, int elem)
+{
+	if (is3(td)) return flof3_interpol_grid(ctx, dst, td, src, sd, elem);
+	return flof_interpol_grid_templ(ctx, dst, td, src, sd, elem);
+}
+int neumann(flof_ctx *ctx, float *grid, flof_dim4 d, int elem, int w)
+{
+	if (is3(d)) return flof3_set_bound_neumann(ctx, grid, d, elem, w);
+	return flof_grid4d_set_bound_neumann(ctx, grid, d, elem, w);
+}
+int of_solve(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof_dim4 d, float wSmooth, float wEnergy,
+             float postVelBlur, float cgAccuracy, float resetBndWidth, int *cgIters, float *cgRes)
+{
+	if (is3(d))
+		return flof3_optical_flow(ctx, vel, i0, i1, NULL, d, wSmooth, wEnergy, postVelBlur, cgAccuracy, resetBndWidth, 1, cgIters,
+		                          cgRes);
+	return flof_optical_flow4d_ex(ctx, vel, i0, i1, NULL, d, wSmooth, wEnergy, postVelBlur, cgAccuracy, resetBndWidth, 1, cgIters,
+	                              cgRes);
+}
+int corr_vels(flof_ctx *ctx, float *dst, float *vel, const float *phiOrg, const float *phiTarget, flof_dim4 d, float threshPhi,
+              float postVelBlur, float resetBndWidth, int maxIter)
+{
+	if (is3(d)) return flof3_corr_vels(ctx, dst, vel, phiOrg, phiTarget, d, threshPhi, postVelBlur, resetBndWidth, maxIter);
+	return flof_corr_vels_of4d(ctx, dst, vel, phiOrg, phiTarget, d, threshPhi, postVelBlur, resetBndWidth, maxIter);
 }
 
 // RAII: shard the level being processed along t over the ranks, restore the caller's state on exit
@@ -196,8 +238,8 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 	if (d.nx > P.minGridSize) {
 		// the coarser level decides about its own sharding; down-sampling runs on complete inputs
 		ShardScope none(ctx, flof_dim4{ 0, 0, 0, 0 });
-		flof_dim4 s = { d.nx / 2, d.ny / 2, d.nz / 2, d.nt / 2 };
-		if (s.nx < 3 || s.ny < 3 || s.nz < 3 || s.nt < 3)
+		flof_dim4 s = { d.nx / 2, d.ny / 2, d.nz / 2, is3(d) ? 1 : d.nt / 2 };  // ref :980-983
+		if (s.nx < 3 || s.ny < 3 || s.nz < 3 || (!is3(d) && s.nt < 3))
 			return flof_fail(ctx, FLOF_ERR_ARG, "opticalFlowMultiscale4d: coarse level %dx%dx%dx%d too small",
 			                 s.nx, s.ny, s.nz, s.nt);
 		const int64_t ns = flof_cells(s);
@@ -205,15 +247,15 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 		MS_RET(velSm.alloc(sizeof(float) * 4 * (size_t)ns, false));
 		MS_RET(i0Sm.alloc(sizeof(float) * (size_t)ns, false));
 		MS_RET(i1Sm.alloc(sizeof(float) * (size_t)ns, false));
-		MS_RET(flof_interpol_grid_templ(ctx, i0Sm.f(), s, i0, d, 1));
-		MS_RET(flof_interpol_grid_templ(ctx, i1Sm.f(), s, i1, d, 1));
-		MS_RET(flof_interpol_grid_templ(ctx, velSm.f(), s, vel, d, 4));
+		MS_RET(resample(ctx, i0Sm.f(), s, i0, d, 1));
+		MS_RET(resample(ctx, i1Sm.f(), s, i1, d, 1));
+		MS_RET(resample(ctx, velSm.f(), s, vel, d, 4));
 		const float half[4] = { 0.5f, 0.5f, 0.5f, 0.5f };
 		MS_RET(flof_grid_mult_const(ctx, velSm.f(), ns, 4, half));
 		float eSm = 0.f;
 		MS_RET(multiscale(ctx, velSm.f(), i0Sm.f(), i1Sm.f(), s, P, level + 1, multiStep, doFinalProject, tr, &eSm));
 		ctx->prof_cells = n;
-		MS_RET(flof_interpol_grid_templ(ctx, vel, d, velSm.f(), s, 4));  // complete (cheap), sliced below
+		MS_RET(resample(ctx, vel, d, velSm.f(), s, 4));  // complete (cheap), sliced below
 		const float two[4] = { 2.f, 2.f, 2.f, 2.f };
 		MS_RET(flof_grid_mult_const(ctx, vel, n, 4, two));
 	}
@@ -223,7 +265,7 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 
 	// pre-warp (ref :1011-1018)
 	MS_RET(advect_cfl(ctx, P.cfl, vel, i0warped.f(), d, 1, 1));
-	MS_RET(flof_grid4d_set_bound_neumann(ctx, i0warped.f(), d, 1, 0));
+	MS_RET(neumann(ctx, i0warped.f(), d, 1, 0));
 	float errCurr = 0.f;
 	MS_RET(flof_calc_ls_diff4d(ctx, i0warped.f(), i1, NULL, d, lsDiffFac, resetBnd, &errCurr));
 
@@ -267,8 +309,8 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 			float cgRes = 0.f;
 			// vs[of] is all zero: the smoothness/Tikhonov rhs terms vanish, so the assembly may
 			// skip reading it (bit-identical: every term is (+-)0 and rhs -= 0 leaves rhs unchanged)
-			MS_RET(flof_optical_flow4d_ex(ctx, vs[of]->f(), i0warped.f(), i1, NULL, d, P.wSmooth, P.wEnergy, velBlur,
-			                              P.cgAccuracy, P.resetBndWidth, 1, &iters, &cgRes));
+			MS_RET(of_solve(ctx, vs[of]->f(), i0warped.f(), i1, d, P.wSmooth, P.wEnergy, velBlur, P.cgAccuracy, P.resetBndWidth,
+			                &iters, &cgRes));
 			tr_solve(tr, iters, n);
 			velBlur *= (float)(3. / 4.);
 			if (velBlur < 2.f) velBlur = 2.f;
@@ -279,7 +321,7 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 			for (int k = of; k >= 0; --k) MS_RET(flof_grid_binary(ctx, tmpVel.f(), vs2[k]->f(), n, 4, FLOF_OP_ADD));
 			MS_RET(flof_memcpy_d2d(ctx, i0warp2.p, i0, rb));
 			MS_RET(advect_cfl(ctx, P.cfl, tmpVel.f(), i0warp2.f(), d, 1, 1));
-			MS_RET(flof_grid4d_set_bound_neumann(ctx, i0warp2.f(), d, 1, 0));
+			MS_RET(neumann(ctx, i0warp2.f(), d, 1, 0));
 			float errC = 0.f;
 			MS_RET(flof_calc_ls_diff4d(ctx, i0warp2.f(), i1, NULL, d, lsDiffFac, resetBnd, &errC));
 			tr_err(tr, errC);
@@ -299,8 +341,8 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 		if (!doProject) {
 			int iters = 0;
 			float cgRes = 0.f;
-			MS_RET(flof_optical_flow4d_ex(ctx, velCurr.f(), i0warped.f(), i1, NULL, d, P.wSmooth, P.wEnergy,
-			                              P.postVelBlur, P.cgAccuracy, P.resetBndWidth, 1, &iters, &cgRes));
+			MS_RET(of_solve(ctx, velCurr.f(), i0warped.f(), i1, d, P.wSmooth, P.wEnergy, P.postVelBlur, P.cgAccuracy,
+			                P.resetBndWidth, &iters, &cgRes));
 			tr_solve(tr, iters, n);
 			MS_RET(flof_grid_binary(ctx, vel, velCurr.f(), n, 4, FLOF_OP_ADD));
 		} else {
@@ -309,8 +351,8 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 			// the projection gathers phiOrg at back-traced positions that leave this rank's slab: complete i0warped first
 			// (after the pre-warp it is valid on the own slices only)
 			MS_RET(flof_allgather_slabs(ctx, i0warped.p, d.nt, sizeof(float) * (size_t)d.nx * d.ny * d.nz));
-			MS_RET(flof_corr_vels_of4d(ctx, velCurr.f(), velTmp2.f(), i0warped.f(), i1, d, projMaxDist, P.postVelBlur,
-			                           P.resetBndWidth, (int)projMaxIter));
+			MS_RET(corr_vels(ctx, velCurr.f(), velTmp2.f(), i0warped.f(), i1, d, projMaxDist, P.postVelBlur, P.resetBndWidth,
+			                 (int)projMaxIter));
 			MS_RET(flof_grid_binary(ctx, vel, velTmp2.f(), n, 4, FLOF_OP_ADD));
 			const float m1[4] = { -1.f, -1.f, -1.f, -1.f };
 			MS_RET(flof_grid_mult_const(ctx, velCurr.f(), n, 4, m1));
@@ -323,15 +365,14 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 		DevBuf velCurr(ctx);
 		MS_RET(velCurr.alloc(vb, true));
 		const float finalProjBlur = 4.f;
-		MS_RET(flof_corr_vels_of4d(ctx, velCurr.f(), vel, i0, i1, d, projMaxDist, finalProjBlur, P.resetBndWidth,
-		                           (int)projMaxIter));
+		MS_RET(corr_vels(ctx, velCurr.f(), vel, i0, i1, d, projMaxDist, finalProjBlur, P.resetBndWidth, (int)projMaxIter));
 	}
 
 	// re-advect and evaluate on the finest level (ref :1155-1170)
 	if (level == 0) {
 		MS_RET(flof_memcpy_d2d(ctx, i0warped.p, i0, rb));
 		MS_RET(advect_cfl(ctx, P.cfl, vel, i0warped.f(), d, 1, 1));
-		MS_RET(flof_grid4d_set_bound_neumann(ctx, i0warped.f(), d, 1, 0));
+		MS_RET(neumann(ctx, i0warped.f(), d, 1, 0));
 		float errFinal = 0.f;
 		MS_RET(flof_calc_ls_diff4d(ctx, i0warped.f(), i1, NULL, d, lsDiffFac, resetBnd, &errFinal));
 		errCurr = errFinal;
@@ -362,6 +403,23 @@ extern "C" int flof_optical_flow_multiscale4d(flof_ctx *ctx, float *vel, const f
 	if (tr) cudaEventElapsedTime(&tr->total_ms, ctx->ev[0], ctx->ev[1]);
 	if (err_out) *err_out = e;
 	if (ctx->nranks > 1) FLOF_RET(flof_comm_p2p_status(ctx, NULL, NULL));  // a timed-out peer wait invalidates the result
+	return FLOF_OK;
+}
+
+// 3D entry of the same driver (flof_optical_flow_multiscale3d in flof_dim3.cu pads / unpads the Vec3 field around it)
+int flof_multiscale_run3d(flof_ctx *ctx, float *vel4, const float *i0, const float *i1, flof_dim4 d,
+                          const flof_multiscale_params *p, flof_multiscale_trace *tr, float *err_out)
+{
+	if (tr) memset(tr, 0, sizeof(*tr));
+	cudaEventRecord(ctx->ev[0], ctx->stream);
+	float e = 0.f;
+	int rc = multiscale(ctx, vel4, i0, i1, d, *p, 0, p->multiStep, p->doFinalProject != 0, tr, &e);
+	cudaEventRecord(ctx->ev[1], ctx->stream);
+	ctx->prof_cells = 0;
+	if (rc != FLOF_OK) return rc;
+	FLOF_CK(cudaEventSynchronize(ctx->ev[1]));
+	if (tr) cudaEventElapsedTime(&tr->total_ms, ctx->ev[0], ctx->ev[1]);
+	if (err_out) *err_out = e;
 	return FLOF_OK;
 }
 

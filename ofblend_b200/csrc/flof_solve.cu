@@ -37,13 +37,14 @@ struct flof_of_consts {
 	float diag;   // 8*wSmooth*mDx2Inv + wEnergy ref :478-480
 };
 
-static flof_of_consts of_consts(float wSmooth, float wEnergy)
+// dim: DIM of the reference's template instantiation (4; 3 for a 3D problem embedded as one slice, flof_dim3.cu)
+static flof_of_consts of_consts(float wSmooth, float wEnergy, int dim = 4)
 {
 	flof_of_consts k;
 	const float mDx2Inv = 1.f;
 	k.offd = -wSmooth * mDx2Inv;
 	volatile float diag = 0.f;
-	diag += (float)(2 * 4) * wSmooth * mDx2Inv;
+	diag += (float)(2 * dim) * wSmooth * mDx2Inv;
 	diag += wEnergy;
 	k.diag = diag;
 	return k;
@@ -705,10 +706,10 @@ extern "C" int flof_seq_stats(flof_ctx *ctx, unsigned long long *stats)
 
 static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, float *zvec, const float *grad,
                   const float *rhs, flof_dim4 d, float wSmooth, float wEnergy, float accuracy,
-                  int maxIter, int *iters, float *relRes, int *status)
+                  int maxIter, int *iters, float *relRes, int *status, int dim = 4)
 {
 	const int64_t cells = flof_cells(d);
-	const flof_of_consts k = of_consts(wSmooth, wEnergy);
+	const flof_of_consts k = of_consts(wSmooth, wEnergy, dim);
 	const int64_t sY = d.nx, sZ = (int64_t)d.nx * d.ny, sT = sZ * d.nz;
 	// sharded level: this rank iterates over its t-slab only; srch needs one ghost slice per side
 	// before every apply, the three scalars of an iteration are all-reduced over the ranks
@@ -825,9 +826,17 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 	return FLOF_OK;
 }
 
+int flof_of_cg_dim(flof_ctx *ctx, float *x, const float *grad, const float *rhs, flof_dim4 d, float wSmooth, float wEnergy,
+                   int dim, float accuracy, int maxIter, int *iters, float *relResidual);
 extern "C" int flof_of_cg(flof_ctx *ctx, float *x, const float *grad, const float *rhs, flof_dim4 d,
                           float wSmooth, float wEnergy, float accuracy, int maxIter, int *iters,
                           float *relResidual)
+{
+	return flof_of_cg_dim(ctx, x, grad, rhs, d, wSmooth, wEnergy, 4, accuracy, maxIter, iters, relResidual);
+}
+// dim = 3: the diagonal constant of the DIM = 3 instantiation (ref :478-480) for an embedded 3D problem
+int flof_of_cg_dim(flof_ctx *ctx, float *x, const float *grad, const float *rhs, flof_dim4 d, float wSmooth, float wEnergy,
+                   int dim, float accuracy, int maxIter, int *iters, float *relResidual)
 {
 	const size_t vb = sizeof(float) * 4 * (size_t)flof_cells(d);
 	void *res = NULL, *srch = NULL, *tmp = NULL, *zv = NULL;
@@ -839,7 +848,7 @@ extern "C" int flof_of_cg(flof_ctx *ctx, float *x, const float *grad, const floa
 	float rr = 0.f;
 	if (rc == FLOF_OK)
 		rc = cg_run(ctx, x, (float *)res, (float *)srch, (float *)tmp, (float *)zv, grad, rhs, d, wSmooth, wEnergy,
-		            accuracy, maxIter, &it, &rr, &st);
+		            accuracy, maxIter, &it, &rr, &st, dim);
 	flof_tmp_free(ctx, res);
 	flof_tmp_free(ctx, srch);
 	flof_tmp_free(ctx, tmp);

@@ -819,6 +819,7 @@ PYBIND11_MODULE(manta, m)
 		c.def(py::init<Solver *, bool>(), py::arg("parent"), py::arg("show") = true, py::keep_alive<1, 2>());
 		bind3(c);
 		m.attr("Vec3Grid") = m.attr("VecGrid");
+		m.attr("MACGrid") = m.attr("VecGrid");  // opticalFlowSimple3d.py passes a MACGrid as the Grid<Vec3> deformation
 	}
 	{
 		py::class_<Grid3T<K_INT>, Grid3> c(m, "IntGrid");
@@ -889,6 +890,83 @@ PYBIND11_MODULE(manta, m)
 	      py::arg("cfl") = 999.f, py::arg("orderTime") = PInt{ 1 }, py::arg("orderSpace") = PInt{ 1 }, py::arg("resetBndWidth") = -1.f,
 	      py::arg("multiStep") = PInt{ 1 }, py::arg("projSizeThresh") = PInt{ 9999 }, py::arg("minGridSize") = PInt{ 10 },
 	      py::arg("doFinalProject") = false);
+
+	// ---- the 3D instantiations (scenes/opticalFlowSimple3d.py): Grid<Real> / Grid<Vec3> on a 3D solver ----
+	// ref opticalFlowMultiscale3d optflow4d.cpp:1175-1188
+	m.def("opticalFlowMultiscale3d",
+	      [](Grid3 &vel, Grid3 &i0, Grid3 &i1, const py::object &rhsT, float wSmooth, float wEnergy, PInt level, float postVelBlur,
+	         float cgAccuracy, PInt blurType, float cfl, PInt orderTime, PInt orderSpace, float resetBndWidth, PInt multiStep,
+	         PInt projSizeThresh, PInt minGridSize, bool doFinalProject) {
+		      const char *fn = "opticalFlowMultiscale3d";
+		      requireKind(vel, K_VEC3, fn, "vel"); requireKind(i0, K_REAL, fn, "i0"); requireKind(i1, K_REAL, fn, "i1");
+		      i0.sameSize(i1, fn); vel.sameRes(i0, fn);
+		      if (vel.d.nz <= 1) errMsg(std::string(fn) + ": 2D grids are not on the B200 path");
+		      if (vel.parent->dt != 1.0f) errMsg("Invalid, only dt 1 for now!");
+		      if (blurType.v != 1) errMsg("NYI");
+		      if (level.v != 0) errMsg(std::string(fn) + ": level must be 0 when called from a scene");
+		      if (optGrid<Grid3>(rhsT, fn)) errMsg(std::string(fn) + ": rhsT is not filled by the multi-scale driver on the B200 path");
+		      (void)orderTime; (void)orderSpace;
+		      flof_multiscale_params p;
+		      flof_multiscale_defaults(&p);
+		      p.wSmooth = wSmooth; p.wEnergy = wEnergy; p.postVelBlur = postVelBlur; p.cgAccuracy = cgAccuracy; p.cfl = cfl;
+		      p.resetBndWidth = resetBndWidth; p.multiStep = multiStep.v; p.projSizeThresh = projSizeThresh.v;
+		      p.minGridSize = minGridSize.v; p.doFinalProject = doFinalProject ? 1 : 0;
+		      flof_multiscale_trace tr;
+		      float err = 0.f;
+		      debMsg(1, "Solving FlOF [" << vel.d.nx << "," << vel.d.ny << "," << vel.d.nz << "] on B200");
+		      CK(flof_optical_flow_multiscale3d(ctx(), vel.f(), i0.f(), i1.f(), vel.d, &p, &tr, &err), fn);
+		      for (int q = 0; q < tr.n_solves && q < 64; ++q) debMsg(1, "ofSolve fix iterations:" << tr.cg_iters[q] << " ");
+		      for (int q = 0; q + 1 < tr.n_errs && q < 63; ++q) debMsg(1, "Current error, step " << q << " = " << tr.errs[q]);
+		      debMsg(1, "Final error=" << err << "  (device time " << tr.total_ms / 1000.f << "s)");
+	      },
+	      py::arg("vel"), py::arg("i0"), py::arg("i1"), py::arg("rhsT") = py::none(), py::arg("wSmooth") = 0.f, py::arg("wEnergy") = 0.f,
+	      py::arg("level") = PInt{ 0 }, py::arg("postVelBlur") = 0.f, py::arg("cgAccuracy") = 1e-04f, py::arg("blurType") = PInt{ 1 },
+	      py::arg("cfl") = 999.f, py::arg("orderTime") = PInt{ 1 }, py::arg("orderSpace") = PInt{ 1 }, py::arg("resetBndWidth") = -1.f,
+	      py::arg("multiStep") = PInt{ 1 }, py::arg("projSizeThresh") = PInt{ 9999 }, py::arg("minGridSize") = PInt{ 10 },
+	      py::arg("doFinalProject") = false);
+	// ref corrVelsOf3d :803-812
+	m.def("corrVelsOf3d",
+	      [](Grid3 &dst, Grid3 &vel, Grid3 &phiOrg, Grid3 &phiCurr, Grid3 &phiTarget, float threshPhi, float threshNorm, float postVelBlur,
+	         float resetBndWidth, PInt maxIter) {
+		      (void)threshNorm;
+		      const char *fn = "corrVelsOf3d";
+		      requireKind(dst, K_VEC3, fn, "dst"); requireKind(vel, K_VEC3, fn, "vel"); requireKind(phiOrg, K_REAL, fn, "phiOrg");
+		      requireKind(phiCurr, K_REAL, fn, "phiCurr"); requireKind(phiTarget, K_REAL, fn, "phiTarget");
+		      vel.sameRes(dst, fn); vel.sameRes(phiOrg, fn); vel.sameRes(phiTarget, fn);
+		      if (vel.d.nz <= 1) errMsg(std::string(fn) + ": 2D grids are not on the B200 path");
+		      CK(flof_corr_vels_of3d(ctx(), dst.f(), vel.f(), phiOrg.f(), phiTarget.f(), vel.d, threshPhi, postVelBlur, resetBndWidth, maxIter.v), fn);
+	      },
+	      py::arg("dst"), py::arg("vel"), py::arg("phiOrg"), py::arg("phiCurr"), py::arg("phiTarget"), py::arg("threshPhi") = 1e10f,
+	      py::arg("threshNorm") = 1e10f, py::arg("postVelBlur") = 0.f, py::arg("resetBndWidth") = -1.f, py::arg("maxIter") = PInt{ 100 });
+	// ref advectSemiLagrangeCfl :863-872 (flags, order and orderSpace are unused by the reference too), advectCent3d :836-846
+	auto advect3 = [](const char *fn, float cfl, Grid3 &vel, Grid3 &grid, float velFactor) {
+		requireKind(vel, K_VEC3, fn, "vel");
+		if (grid.kind != K_REAL && grid.kind != K_VEC3) errMsg("AdvectSemiLagrange3d: Grid Type is not supported (only Real, Vec3)");
+		vel.sameRes(grid, fn);
+		if (vel.d.nz <= 1) errMsg(std::string(fn) + ": 2D grids are not on the B200 path");
+		if (vel.parent->dt != 1.0f) errMsg(std::string(fn) + ": only dt 1 on the B200 path");
+		CK(flof_advect_semi_lagrange_cfl3d(ctx(), cfl, vel.f(), grid.f(), grid.elem, vel.d, velFactor), fn);
+	};
+	m.def("advectSemiLagrangeCfl",
+	      [advect3](float cfl, Grid3 &flags, Grid3 &vel, Grid3 &grid, PInt order, float velFactor, PInt orderSpace) {
+		      (void)flags; (void)order; (void)orderSpace;
+		      advect3("advectSemiLagrangeCfl", cfl, vel, grid, velFactor);
+	      },
+	      py::arg("cfl"), py::arg("flags"), py::arg("vel"), py::arg("grid"), py::arg("order") = PInt{ 1 }, py::arg("velFactor") = 1.f,
+	      py::arg("orderSpace") = PInt{ 1 });
+	m.def("advectCent3d", [advect3](Grid3 &vel, Grid3 &grid) { advect3("advectCent3d", 3.0e38f, vel, grid, 1.f); }, py::arg("vel"),
+	      py::arg("grid"));
+	// ref calcLsDiff3d :928-933
+	m.def("calcLsDiff3d",
+	      [](Grid3 &i0, Grid3 &i1, const py::object &out, float correction, PInt bnd) {
+		      Grid3 *o = optGrid<Grid3>(out, "calcLsDiff3d");
+		      requireKind(i0, K_REAL, "calcLsDiff3d", "i0"); requireKind(i1, K_REAL, "calcLsDiff3d", "i1"); i0.sameSize(i1, "calcLsDiff3d");
+		      if (o) { requireKind(*o, K_REAL, "calcLsDiff3d", "out"); i0.sameSize(*o, "calcLsDiff3d"); }
+		      float r = 0.f;
+		      CK(flof_calc_ls_diff3d(ctx(), i0.f(), i1.f(), o ? o->f() : nullptr, i0.d, correction, bnd.v, &r), "calcLsDiff3d");
+		      return r;
+	      },
+	      py::arg("i0"), py::arg("i1"), py::arg("out") = py::none(), py::arg("correction") = 1.f, py::arg("bnd") = PInt{ 0 });
 
 	// ref opticalFlow4d :2110
 	m.def("opticalFlow4d",

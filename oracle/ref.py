@@ -180,6 +180,50 @@ def optical_flow_multiscale4d(vel, i0, i1, wSmooth=0., wEnergy=0., postVelBlur=0
     return v
 
 
+# ---- 3D instantiations: numpy layout [z, y, x(, 3)]
+def _d3v(a):
+    return (a.shape[2], a.shape[1], a.shape[0])
+
+
+def optical_flow_multiscale3d(vel, i0, i1, wSmooth=0., wEnergy=0., postVelBlur=0., cgAccuracy=1e-4, cfl=999.,
+                              resetBndWidth=-1., multiStep=1, projSizeThresh=9999, minGridSize=10, doFinalProject=False):
+    v = _f32(vel).copy()
+    i0 = _f32(i0)
+    i1 = _f32(i1)
+    _chk(lib().ref_optical_flow_multiscale3d(
+        _i4(_d3v(i0)), _p(v), _p(i0), _p(i1), C.c_float(wSmooth), C.c_float(wEnergy), C.c_float(postVelBlur),
+        C.c_float(cgAccuracy), C.c_float(cfl), C.c_float(resetBndWidth), int(multiStep), int(projSizeThresh),
+        int(minGridSize), int(bool(doFinalProject))))
+    return v
+
+
+def corr_vels_of3d(dst, vel, phiOrg, phiTarget, threshPhi=1e10, postVelBlur=0., resetBndWidth=-1., maxIter=100):
+    d = _f32(dst).copy()
+    v = _f32(vel).copy()
+    po = _f32(phiOrg)
+    pt = _f32(phiTarget)
+    _chk(lib().ref_corr_vels_of3d(_i4(_d3v(po)), _p(d), _p(v), _p(po), _p(pt), C.c_float(threshPhi),
+                                  C.c_float(postVelBlur), C.c_float(resetBndWidth), int(maxIter)))
+    return d, v
+
+
+def advect_semi_lagrange_cfl3d(cfl, vel, grid, velFactor=1.):
+    v = _f32(vel)
+    g = _f32(grid).copy()
+    _chk(lib().ref_advect_semi_lagrange_cfl3d(_i4(_d3v(v)), C.c_float(cfl), _p(v), _p(g), 3 if g.ndim == 4 else 1,
+                                              C.c_float(velFactor)))
+    return g
+
+
+def calc_ls_diff3d(i0, i1, correction=1., bnd=0, want_out=False):
+    a = _f32(i0)
+    b = _f32(i1)
+    out = np.zeros(a.shape, np.float32) if want_out else None
+    r = C.c_float(0)
+    _chk(lib().ref_calc_ls_diff3d(_i4(_d3v(a)), _p(a), _p(b), _p(out), C.c_float(correction), int(bnd), C.byref(r)))
+    return (r.value, out) if want_out else r.value
+
+
 def extrap4d_ls_simple(phi, distance=4, inside=False, want_marker=False):
     p = _f32(phi).copy()
     if want_marker:

@@ -319,6 +319,81 @@ int ref_optical_flow_multiscale4d(const int *d, float *vel, const float *i0,
 	REF_CATCH
 }
 
+/* ---- the 3D instantiations: Grid<Real> / Grid<Vec3> on a plain 3D solver ---- */
+#define SOLVER3(d) FluidSolver solver(Vec3i((d)[0], (d)[1], (d)[2]), 3, -1)
+
+/* optflow4d.cpp:1175 opticalFlowMultiscale3d */
+int ref_optical_flow_multiscale3d(const int *d3, float *vel3, const float *i0, const float *i1, float wSmooth,
+                                  float wEnergy, float postVelBlur, float cgAccuracy, float cfl, float resetBndWidth,
+                                  int multiStep, int projSizeThresh, int minGridSize, int doFinalProject)
+{
+	REF_TRY
+	SOLVER3(d3);
+	Grid<Vec3> v(&solver);
+	Grid<Real> a(&solver), b(&solver);
+	put3(v, vel3);
+	put3(a, i0);
+	put3(b, i1);
+	opticalFlowMultiscale3d(v, a, b, NULL, wSmooth, wEnergy, 0, postVelBlur, cgAccuracy, 1, cfl, 1, 1, resetBndWidth,
+	                        multiStep, projSizeThresh, minGridSize, doFinalProject != 0);
+	get3(v, vel3);
+	REF_CATCH
+}
+
+/* optflow4d.cpp:803 corrVelsOf3d */
+int ref_corr_vels_of3d(const int *d3, float *dst3, float *vel3, const float *phiOrg, const float *phiTarget,
+                       float threshPhi, float postVelBlur, float resetBndWidth, int maxIter)
+{
+	REF_TRY
+	SOLVER3(d3);
+	Grid<Vec3> gd(&solver), gv(&solver);
+	Grid<Real> po(&solver), pt(&solver);
+	put3(gd, dst3);
+	put3(gv, vel3);
+	put3(po, phiOrg);
+	put3(pt, phiTarget);
+	corrVelsOf3d(gd, gv, po, po, pt, threshPhi, 1e10, postVelBlur, resetBndWidth, maxIter);
+	get3(gd, dst3);
+	get3(gv, vel3);
+	REF_CATCH
+}
+
+/* optflow4d.cpp:863 advectSemiLagrangeCfl (elem 1: Grid<Real>, 3: Grid<Vec3> payload) */
+int ref_advect_semi_lagrange_cfl3d(const int *d3, float cfl, const float *vel3, float *grid, int elem, float velFactor)
+{
+	REF_TRY
+	SOLVER3(d3);
+	FlagGrid flags(&solver);
+	Grid<Vec3> v(&solver);
+	put3(v, vel3);
+	if (elem == 3) {
+		Grid<Vec3> g(&solver);
+		put3(g, grid);
+		advectSemiLagrangeCfl(cfl, flags, v, &g, 1, velFactor, 1);
+		get3(g, grid);
+	} else {
+		Grid<Real> g(&solver);
+		put3(g, grid);
+		advectSemiLagrangeCfl(cfl, flags, v, &g, 1, velFactor, 1);
+		get3(g, grid);
+	}
+	REF_CATCH
+}
+
+/* optflow4d.cpp:928 calcLsDiff3d */
+int ref_calc_ls_diff3d(const int *d3, const float *i0, const float *i1, float *out, float correction, int bnd,
+                       float *result)
+{
+	REF_TRY
+	SOLVER3(d3);
+	Grid<Real> a(&solver), b(&solver), o(&solver);
+	put3(a, i0);
+	put3(b, i1);
+	*result = calcLsDiff3d(a, b, out ? &o : NULL, correction, bnd);
+	if (out) get3(o, out);
+	REF_CATCH
+}
+
 /* optflow4d.cpp:1361 extrap4dLsSimple */
 int ref_extrap4d_ls_simple(const int *d, float *phi, int distance, int inside)
 {

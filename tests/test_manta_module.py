@@ -152,3 +152,63 @@ def test_defo_volumes_and_unoptimised_lookup_through_the_module(tmp_path):
     host = os.path.join(ROOT, "ofblend_b200", "host")
     p = subprocess.run([sys.executable, "-c", DEFOVOL_SNIPPET, host, ROOT, str(tmp_path)], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode == 0 and "MANTA_DEFOVOL_OK" in p.stdout, p.stdout[-2000:] + "\n" + p.stderr[-3000:]
+
+
+DIM3_SNIPPET = r"""
+import os, sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2]); sys.path.insert(0, os.path.join(sys.argv[2], "tests"))
+from manta import *
+from conftest import DIM3_CASES, sdf_pair3
+gold = np.load(os.path.join(sys.argv[2], "tests", "golden", "dim3_ops.npz"))
+
+def put(g, a):
+    g.fromBytes(np.ascontiguousarray(a).tobytes())
+
+def get(g, shape, dt=np.float32):
+    return np.frombuffer(g.toNumpyBytes(), dtype=dt).reshape(shape)
+
+# the call sequence of scenes/opticalFlowSimple3d.py:12-64 (inputs uploaded instead of Box.computeLevelset)
+dims, params = DIM3_CASES["scene"]
+A, B = sdf_pair3(dims)
+gs = vec3(*dims)
+s = Solver(name='main', gridSize=gs, dim=3)
+flags = s.create(FlagGrid)
+phi, i0, i1 = s.create(LevelsetGrid), s.create(LevelsetGrid), s.create(LevelsetGrid)
+vel = s.create(MACGrid)
+put(i0, A); put(i1, B)
+opticalFlowMultiscale3d(i0=i0, i1=i1, vel=vel, wSmooth=0.5, wEnergy=0.0001, multiStep=4)
+phi.copyFrom(i0)
+advectSemiLagrangeCfl(flags=flags, vel=vel, grid=phi, order=1, velFactor=(float)(1.0), cfl=999)
+sh = A.shape
+assert np.array_equal(get(vel, sh + (3,)), gold["ms_scene_vel"])
+assert np.array_equal(get(phi, sh), gold["ms_scene_adv"])
+e0, e1 = calcLsDiff3d(i0=i0, i1=i1, correction=20.), calcLsDiff3d(i0=phi, i1=i1, correction=20.)
+assert e1 < 0.5 * e0, (e0, e1)      # the deformation brings i0 onto i1
+# advectCent3d = one semi-Lagrangian step (ref :836-846)
+p2 = s.create(LevelsetGrid); p2.copyFrom(i0)
+advectCent3d(vel, p2)
+assert np.array_equal(get(p2, sh), gold["ms_scene_adv"])
+# corrVelsOf3d on the second fixture
+D = (20, 18, 16); SH = (16, 18, 20)
+s2 = Solver(name='c', gridSize=vec3(*D), dim=3)
+a0, a1 = sdf_pair3(D)
+dst, v, q0, q1 = s2.create(VecGrid), s2.create(VecGrid), s2.create(RealGrid), s2.create(RealGrid)
+put(q0, a0); put(q1, a1)
+put(v, (np.random.default_rng(12).standard_normal(SH + (3,)) * 0.5).astype(np.float32))
+corrVelsOf3d(dst, v, q0, q0, q1, 4., 1e10, 2., 0.1, 40)
+assert np.array_equal(get(dst, SH + (3,)), gold["corr_dst"]) and np.array_equal(get(v, SH + (3,)), gold["corr_vel"])
+try:
+    opticalFlowMultiscale3d(i0=i0, i1=q1, vel=vel)
+    raise SystemExit("size mismatch not detected")
+except RuntimeError:
+    pass
+print("MANTA_DIM3_OK")
+"""
+
+
+def test_3d_plugins_through_the_module():
+    """opticalFlowMultiscale3d / advectSemiLagrangeCfl / advectCent3d / calcLsDiff3d / corrVelsOf3d called like
+    scenes/opticalFlowSimple3d.py does, results bit-identical to the reference's (tests/golden/dim3_ops.npz)."""
+    host = os.path.join(ROOT, "ofblend_b200", "host")
+    p = subprocess.run([sys.executable, "-c", DIM3_SNIPPET, host, ROOT], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0 and "MANTA_DIM3_OK" in p.stdout, p.stdout[-2000:] + "\n" + p.stderr[-3000:]

@@ -46,7 +46,7 @@ def main():
             py, pz, q.any(axis=(2, 4, 6)).mean(), q.any(axis=(2, 4)).sum() / max(1, q.any(axis=(2, 4, 6)).sum() * 32), py, pz,
             q.any(axis=(2, 4)).mean()))
     nz = (v != 0).any(axis=-1)
-    for s in (0, 1, 2, 4, 8):
+    for s in (0, 1, 2, 4, 8, 16, 32, 64):
         if s:
             ctx.cv_expol_blur4d(dst, mk, s - prev)
         prev = s
