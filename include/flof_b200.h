@@ -315,7 +315,7 @@ int flof_load_advect_time_slice_unopt(flof_ctx *ctx, const float *defo_vec4, flo
                                       float *dbgVel3, float *dbgVelT);
 /* ---- 3D instantiations of the optical-flow templates (scenes/opticalFlowSimple3d.py) ----------------
  * Grids are nx*ny*nz arrays, x fastest; velocities are Vec3 AoS (3 floats per cell) like the reference's Grid<Vec3>.
- * 2D grids (nz == 1) are not built. */
+ * nz == 1 is a 2D grid (the DIM = 2 instantiation of scenes/ofblend2dTest.py): the reference's is3D() switches apply. */
 /* ref: opticalFlowMultiscale3d optflow4d.cpp:1175-1188 (template :936-1173 with Grid<Real> / Grid<Vec3>).  Synchronises. */
 int flof_optical_flow_multiscale3d(flof_ctx *ctx, float *vel_vec3, const float *i0, const float *i1, flof_dim3 d,
                                    const flof_multiscale_params *p, flof_multiscale_trace *tr, float *err_out);

@@ -44,7 +44,9 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	if (!flof_cell_ijkt(d, i, j, k, t)) return;
 	// KERNEL(fourd, bnd = 1): a one-slice grid is not 4D in the reference (kernel.h:62-68), t is unbounded there --
 	// the 3D instantiation gaussianBlurGeneric<Grid<Vec3>> runs through this kernel with d.nt == 1
-	if (d.nt == 1 ? !(i >= 1 && j >= 1 && k >= 1 && i < d.nx - 1 && j < d.ny - 1 && k < d.nz - 1) : !flof_in_bounds(d, i, j, k, t, 1))
+	// (and a one-plane grid is 2D: z unbounded as well)
+	if (d.nt == 1 ? !(i >= 1 && j >= 1 && i < d.nx - 1 && j < d.ny - 1 && (d.nz == 1 || (k >= 1 && k < d.nz - 1)))
+	              : !flof_in_bounds(d, i, j, k, t, 1))
 		return;
 	T val = blur_zero<T>();
 	float weight = 0.f;

@@ -371,7 +371,7 @@ __device__ __forceinline__ T flof_interpol3d(const T *__restrict__ data, flof_di
 	if (d.nz > 1) {
 		if (zi >= d.nz - 1) { zi = d.nz - 2; f0 = 0.f; f1 = 1.f; }
 	}
-	const int64_t X = 1, Y = d.nx, Z = (int64_t)d.nx * d.ny;
+	const int64_t X = 1, Y = d.nx, Z = d.nz > 1 ? (int64_t)d.nx * d.ny : 0;  // mStrideZ of a 2D grid is 0 (grid.cpp:64)
 	const T *p = data + ((int64_t)xi + Y * yi + Z * zi);
 	return ((__ldg(p) * t0 + __ldg(p + Y) * t1) * s0 + (__ldg(p + X) * t0 + __ldg(p + X + Y) * t1) * s1) * f0 +
 	       ((__ldg(p + Z) * t0 + __ldg(p + Y + Z) * t1) * s0 +

@@ -15,7 +15,8 @@
 //    ((2*DIM) * wSmooth + wEnergy, ref :478-480) and is passed explicitly.
 //  * Everything else is a one-thread-per-cell 3D kernel below (3D grids are small: performance is not on the north-star
 //    path, parity is).  The multi-scale driver is the same function as in 4D (flof_multiscale.cu) with a 3D operator table.
-// 2D grids (nz == 1, DIM = 2 in the reference) are not built.
+//  * 2D grids (nz == 1, the reference's DIM = 2 instantiation used by scenes/ofblend2dTest.py) take the same route: every
+//    kernel below follows the reference's `is3D()` switches, the solve embeds the plane in z and in t.
 #include <math.h>
 
 #include "flof_common.cuh"
@@ -30,8 +31,9 @@ int flof_multiscale_run3d(flof_ctx *ctx, float *vel4, const float *i0, const flo
 namespace {
 
 __device__ __forceinline__ bool in3(const flof_dim4 &d, int i, int j, int k, int b)
-{  // ref GridBase::isInBounds(Vec3i, bnd) grid.h:630-640 for a 3D grid
-	return i >= b && j >= b && k >= b && i < d.nx - b && j < d.ny - b && k < d.nz - b;
+{  // ref GridBase::isInBounds(Vec3i, bnd) grid.h:630-640: z is bounded on a 3D grid, must be 0 on a 2D one (nz == 1)
+	if (!(i >= b && j >= b && i < d.nx - b && j < d.ny - b)) return false;
+	return d.nz > 1 ? (k >= b && k < d.nz - b) : (k == 0);
 }
 __device__ __forceinline__ flof_dim3 d3of(const flof_dim4 &d)
 {
@@ -62,7 +64,8 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 {
 	int i, j, k, t;
 	if (!flof_cell_ijkt(td, i, j, k, t)) return;
-	const float px = (float)i * fac.x + off.x, py = (float)j * fac.y + off.y, pz = (float)k * fac.z + off.z;
+	const float px = (float)i * fac.x + off.x, py = (float)j * fac.y + off.y;
+	const float pz = sd.nz > 1 ? (float)k * fac.z + off.z : 0.f;  // if (!source.is3D()) pos[2] = 0, grid.h:836
 	dst[flof_idx(td, i, j, k, 0)] = flof_interpol3d<T>(src, sd, px, py, pz);
 }
 
@@ -98,8 +101,10 @@ __global__ void __launch_bounds__(FLOF_BLOCK) k3_set_bound_neumann(T *grid, flof
 	if (i >= d.nx - 1 - w) { si = d.nx - 1 - w - 1; set = true; }
 	if (j <= w) { sj = w + 1; set = true; }
 	if (j >= d.ny - 1 - w) { sj = d.ny - 1 - w - 1; set = true; }
-	if (k <= w) { sk = w + 1; set = true; }
-	if (k >= d.nz - 1 - w) { sk = d.nz - 1 - w - 1; set = true; }
+	if (d.nz > 1) {  // grid.is3D()
+		if (k <= w) { sk = w + 1; set = true; }
+		if (k >= d.nz - 1 - w) { sk = d.nz - 1 - w - 1; set = true; }
+	}
 	// the source cell has no clamped coordinate left, so it is never written by this launch
 	if (set) grid[flof_idx(d, i, j, k, 0)] = grid[flof_idx(d, si, sj, sk, 0)];
 }
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK) k3_set_bound_zero(float4 *grid, fl
 {
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t)) return;
-	const bool bnd = i <= w || i >= d.nx - 1 - w || j <= w || j >= d.ny - 1 - w || k <= w || k >= d.nz - 1 - w;
+	const bool bnd = i <= w || i >= d.nx - 1 - w || j <= w || j >= d.ny - 1 - w || (d.nz > 1 && (k <= w || k >= d.nz - 1 - w));
 	if (bnd) grid[flof_idx(d, i, j, k, 0)] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 // ref :544-551: everything outside isInBounds(resetBnd) -> 0
@@ -135,7 +140,8 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	const float h = 0.5f;
 	float n0 = flof_interpol3d<float>(phiOrg, s, px + h, py, pz) - flof_interpol3d<float>(phiOrg, s, px - h, py, pz);
 	float n1 = flof_interpol3d<float>(phiOrg, s, px, py + h, pz) - flof_interpol3d<float>(phiOrg, s, px, py - h, pz);
-	float n2 = flof_interpol3d<float>(phiOrg, s, px, py, pz + h) - flof_interpol3d<float>(phiOrg, s, px, py, pz - h);
+	float n2 = 0.f;  // `VEC n;` is zero-initialised (vectorbase.h:92); n[2] is only set if (phi.is3D()), ref :662-665
+	if (d.nz > 1) n2 = flof_interpol3d<float>(phiOrg, s, px, py, pz + h) - flof_interpol3d<float>(phiOrg, s, px, py, pz - h);
 	{  // normalize(Vector3D), ref util/vectorbase.h:401-415
 		const float l = n0 * n0 + n1 * n1 + n2 * n2;
 		const double eps2 = (double)(FLOF_VECTOR_EPSILON * FLOF_VECTOR_EPSILON);
@@ -185,7 +191,8 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 	marker[c] = 1.f;
 }
 
-// ---- knCvExpolBlur3d :627-638: 27 taps in (zk, yj, xi) order, * (1./27.0); other cells keep the copy ------------------
+// ---- knCvExpolBlur3d :627-638: 27 taps in (zk, yj, xi) order, * (1./27.0); knCvExpolBlur2d :639-649: 9 taps, * (1./9.0);
+// other cells keep the copy -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k3_cv_expol_blur(const float4 *__restrict__ a, float4 *__restrict__ tmp, const float *__restrict__ mark, flof_kd d)
 {
@@ -197,7 +204,8 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 		return;
 	}
 	float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-	for (int zk = k - 1; zk <= k + 1; ++zk)
+	const int z0 = d.nz > 1 ? k - 1 : 0, z1 = d.nz > 1 ? k + 1 : 0;
+	for (int zk = z0; zk <= z1; ++zk)
 		for (int yj = j - 1; yj <= j + 1; ++yj) {
 			const float4 *row = a + flof_idx(d, i - 1, yj, zk, 0);
 #pragma unroll
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 				val.x += q.x; val.y += q.y; val.z += q.z;
 			}
 		}
-	const double f = 1. / 27.0;
+	const double f = d.nz > 1 ? 1. / 27.0 : 1. / 9.0;
 	tmp[c] = make_float4((float)(val.x * f), (float)(val.y * f), (float)(val.z * f), 0.f);
 }
 
@@ -215,12 +223,12 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k3_copy_back(float4 *__restrict__ vel, const float4 *__restrict__ x, const float4 *__restrict__ rhs,
                  float *__restrict__ rhsT, int64_t cells, float mDx)
-{  // ref :520-529 on the middle slice
+{  // ref :520-529 on the middle slice (x, rhs point at it)
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += stride) {
-		const float4 v = __ldg(x + cells + c);
+		const float4 v = __ldg(x + c);
 		vel[c] = make_float4(v.x / mDx, v.y / mDx, v.z / mDx, 0.f);
-		if (rhsT) rhsT[c] = __ldg(rhs + cells + c).x;
+		if (rhsT) rhsT[c] = __ldg(rhs + c).x;
 	}
 }
 
@@ -300,7 +308,7 @@ int flof3_advect_cfl(flof_ctx *ctx, float cfl, const float *vel, float *grid, fl
 
 int flof3_set_bound_neumann(flof_ctx *ctx, float *grid, flof_dim4 d, int elem, int w)
 {
-	FLOF_ARG(d.nx >= 2 * w + 3 && d.ny >= 2 * w + 3 && d.nz >= 2 * w + 3, "setBoundNeumann: grid too small for width %d", w);
+	FLOF_ARG(d.nx >= 2 * w + 3 && d.ny >= 2 * w + 3 && (d.nz == 1 || d.nz >= 2 * w + 3), "setBoundNeumann: grid too small for width %d", w);
 	dim3 g;
 	const flof_kd kd = kd3(d, &g);
 	if (elem == 4)
@@ -310,37 +318,40 @@ int flof3_set_bound_neumann(flof_ctx *ctx, float *grid, flof_dim4 d, int elem, i
 	return FLOF_OK;
 }
 
-// opticalFlowDim<Grid<Real>, Grid<Vec3>, 3> :361-553
+// opticalFlowDim<Grid<Real>, Grid<Vec3>, 3> :361-553; a 2D grid (nz == 1, DIM = 2) is embedded the same way in z AND t:
+// the centre of a 3 x 3 block of copies, diagonal constant of DIM = 2
 int flof3_optical_flow(flof_ctx *ctx, float *vel, const float *i0, const float *i1, float *rhsT, flof_dim4 d, float wSmooth,
                        float wEnergy, float postVelBlur, float cgAccuracy, float resetBndWidth, int vel_is_zero, int *cgIters,
                        float *cgRes)
 {
-	FLOF_ARG(d.nx >= 3 && d.ny >= 3 && d.nz >= 3 && d.nt == 1, "opticalFlow (3D): grid too small");
+	FLOF_ARG(d.nx >= 3 && d.ny >= 3 && (d.nz >= 3 || d.nz == 1) && d.nt == 1, "opticalFlow (3D): grid too small");
 	const int64_t cells = flof_cells(d);
-	const flof_dim4 e = { d.nx, d.ny, d.nz, 3 };  // the embedding: slices 0 and 2 repeat slice 1
+	const bool two = d.nz == 1;
+	const flof_dim4 e = { d.nx, d.ny, two ? 3 : d.nz, 3 };  // the embedding: the outer slices repeat the middle one
+	const int copies = two ? 9 : 3, mid = two ? 4 : 1;
 	const size_t rb = sizeof(float) * (size_t)cells, vb = rb * 4;
 	Tmp i0e(ctx), i1e(ctx), ve(ctx), grad(ctx), rhs(ctx), x(ctx);
-	FLOF_RET(i0e.alloc(3 * rb, false));
-	FLOF_RET(i1e.alloc(3 * rb, false));
-	for (int s = 0; s < 3; ++s) {
+	FLOF_RET(i0e.alloc(copies * rb, false));
+	FLOF_RET(i1e.alloc(copies * rb, false));
+	for (int s = 0; s < copies; ++s) {
 		FLOF_RET(flof_memcpy_d2d(ctx, (char *)i0e.p + s * rb, i0, rb));
 		FLOF_RET(flof_memcpy_d2d(ctx, (char *)i1e.p + s * rb, i1, rb));
 	}
 	if (!vel_is_zero) {
-		FLOF_RET(ve.alloc(3 * vb, false));
-		for (int s = 0; s < 3; ++s) FLOF_RET(flof_memcpy_d2d(ctx, (char *)ve.p + s * vb, vel, vb));
+		FLOF_RET(ve.alloc(copies * vb, false));
+		for (int s = 0; s < copies; ++s) FLOF_RET(flof_memcpy_d2d(ctx, (char *)ve.p + s * vb, vel, vb));
 	}
-	FLOF_RET(grad.alloc(3 * vb, false));
-	FLOF_RET(rhs.alloc(3 * vb, false));
-	FLOF_RET(x.alloc(3 * vb, false));
+	FLOF_RET(grad.alloc(copies * vb, false));
+	FLOF_RET(rhs.alloc(copies * vb, false));
+	FLOF_RET(x.alloc(copies * vb, false));
 	FLOF_RET(flof_of_assemble(ctx, grad.f(), rhs.f(), i0e.f(), i1e.f(), vel_is_zero ? NULL : ve.f(), e, wSmooth, wEnergy));
 	int it = 0;
 	float rr = 1e10f;
-	FLOF_RET(flof_of_cg_dim(ctx, x.f(), grad.f(), rhs.f(), e, wSmooth, wEnergy, 3, cgAccuracy, 1000, &it, &rr));
-	if (rr != rr) FLOF_RET(flof_memset0(ctx, x.p, 3 * vb));  // ref :509-514
+	FLOF_RET(flof_of_cg_dim(ctx, x.f(), grad.f(), rhs.f(), e, wSmooth, wEnergy, two ? 2 : 3, cgAccuracy, 1000, &it, &rr));
+	if (rr != rr) FLOF_RET(flof_memset0(ctx, x.p, copies * vb));  // ref :509-514
 	const float mDx = (float)(1. / d.nx);
-	FLOF_LAUNCH(k3_copy_back, flof_flat_blocks(ctx, cells, 8), FLOF_BLOCK, 0, (float4 *)vel, (const float4 *)x.p,
-	            (const float4 *)rhs.p, rhsT, cells, mDx);
+	FLOF_LAUNCH(k3_copy_back, flof_flat_blocks(ctx, cells, 8), FLOF_BLOCK, 0, (float4 *)vel, (const float4 *)x.p + mid * cells,
+	            (const float4 *)rhs.p + mid * cells, rhsT, cells, mDx);
 	if (postVelBlur > 0.f) FLOF_RET(flof_gaussian_blur4d_impl(ctx, vel, d, 4, (float)(0.5 * postVelBlur), 1));
 	if (resetBndWidth > 0.f) {
 		const int resetBnd = (int)(resetBndWidth * d.nx) + 1;
@@ -357,7 +368,7 @@ int flof3_optical_flow(flof_ctx *ctx, float *vel, const float *i0, const float *
 int flof3_corr_vels(flof_ctx *ctx, float *dst, float *vel, const float *phiOrg, const float *phiTarget, flof_dim4 d,
                     float threshPhi, float postVelBlur, float resetBndWidth, int maxIter)
 {
-	FLOF_ARG(d.nx >= 5 && d.ny >= 5 && d.nz >= 5 && d.nt == 1, "corrVelsOf3d: grid too small");
+	FLOF_ARG(d.nx >= 5 && d.ny >= 5 && (d.nz >= 5 || d.nz == 1) && d.nt == 1, "corrVelsOf3d: grid too small");
 	const int64_t cells = flof_cells(d);
 	const size_t vb = sizeof(float) * 4 * (size_t)cells;
 	const float blurThreshold = 0.98f;
@@ -412,7 +423,7 @@ extern "C" int flof_optical_flow_multiscale3d(flof_ctx *ctx, float *vel3, const 
                                               const flof_multiscale_params *p, flof_multiscale_trace *tr, float *err_out)
 {
 	FLOF_ARG(p != NULL, "opticalFlowMultiscale3d: params is NULL");
-	FLOF_ARG(d.nx >= 3 && d.ny >= 3 && d.nz >= 3, "opticalFlowMultiscale3d: grid too small (2D grids are not built)");
+	FLOF_ARG(d.nx >= 3 && d.ny >= 3 && (d.nz >= 3 || d.nz == 1), "opticalFlowMultiscale3d: grid too small");
 	const int64_t cells = flof_cells3(d);
 	Tmp v4(ctx);
 	FLOF_RET(v4.alloc(sizeof(float) * 4 * (size_t)cells, false));
@@ -439,7 +450,7 @@ extern "C" int flof_advect_semi_lagrange_cfl3d(flof_ctx *ctx, float cfl, const f
                                                float velFactor)
 {
 	FLOF_ARG(elem == 1 || elem == 3, "advectSemiLagrangeCfl: Grid Type is not supported (only Real, Vec3)");
-	FLOF_ARG(d.nx >= 3 && d.ny >= 3 && d.nz >= 3, "advectSemiLagrangeCfl: grid too small (2D grids are not built)");
+	FLOF_ARG(d.nx >= 3 && d.ny >= 3 && (d.nz >= 3 || d.nz == 1), "advectSemiLagrangeCfl: grid too small");
 	FLOF_ARG(cfl > 0.f, "advectSemiLagrangeCfl: cfl must be positive");
 	const int64_t cells = flof_cells3(d);
 	Tmp v4(ctx), g4(ctx);

@@ -238,8 +238,8 @@ int multiscale(flof_ctx *ctx, float *vel, const float *i0, const float *i1, flof
 	if (d.nx > P.minGridSize) {
 		// the coarser level decides about its own sharding; down-sampling runs on complete inputs
 		ShardScope none(ctx, flof_dim4{ 0, 0, 0, 0 });
-		flof_dim4 s = { d.nx / 2, d.ny / 2, d.nz / 2, is3(d) ? 1 : d.nt / 2 };  // ref :980-983
-		if (s.nx < 3 || s.ny < 3 || s.nz < 3 || (!is3(d) && s.nt < 3))
+		flof_dim4 s = { d.nx / 2, d.ny / 2, d.nz > 1 ? d.nz / 2 : 1, is3(d) ? 1 : d.nt / 2 };  // ref :980-983
+		if (s.nx < 3 || s.ny < 3 || (d.nz > 1 && s.nz < 3) || (!is3(d) && s.nt < 3))
 			return flof_fail(ctx, FLOF_ERR_ARG, "opticalFlowMultiscale4d: coarse level %dx%dx%dx%d too small",
 			                 s.nx, s.ny, s.nz, s.nt);
 		const int64_t ns = flof_cells(s);

@@ -900,7 +900,6 @@ PYBIND11_MODULE(manta, m)
 		      const char *fn = "opticalFlowMultiscale3d";
 		      requireKind(vel, K_VEC3, fn, "vel"); requireKind(i0, K_REAL, fn, "i0"); requireKind(i1, K_REAL, fn, "i1");
 		      i0.sameSize(i1, fn); vel.sameRes(i0, fn);
-		      if (vel.d.nz <= 1) errMsg(std::string(fn) + ": 2D grids are not on the B200 path");
 		      if (vel.parent->dt != 1.0f) errMsg("Invalid, only dt 1 for now!");
 		      if (blurType.v != 1) errMsg("NYI");
 		      if (level.v != 0) errMsg(std::string(fn) + ": level must be 0 when called from a scene");
@@ -933,7 +932,6 @@ PYBIND11_MODULE(manta, m)
 		      requireKind(dst, K_VEC3, fn, "dst"); requireKind(vel, K_VEC3, fn, "vel"); requireKind(phiOrg, K_REAL, fn, "phiOrg");
 		      requireKind(phiCurr, K_REAL, fn, "phiCurr"); requireKind(phiTarget, K_REAL, fn, "phiTarget");
 		      vel.sameRes(dst, fn); vel.sameRes(phiOrg, fn); vel.sameRes(phiTarget, fn);
-		      if (vel.d.nz <= 1) errMsg(std::string(fn) + ": 2D grids are not on the B200 path");
 		      CK(flof_corr_vels_of3d(ctx(), dst.f(), vel.f(), phiOrg.f(), phiTarget.f(), vel.d, threshPhi, postVelBlur, resetBndWidth, maxIter.v), fn);
 	      },
 	      py::arg("dst"), py::arg("vel"), py::arg("phiOrg"), py::arg("phiCurr"), py::arg("phiTarget"), py::arg("threshPhi") = 1e10f,
@@ -943,7 +941,6 @@ PYBIND11_MODULE(manta, m)
 		requireKind(vel, K_VEC3, fn, "vel");
 		if (grid.kind != K_REAL && grid.kind != K_VEC3) errMsg("AdvectSemiLagrange3d: Grid Type is not supported (only Real, Vec3)");
 		vel.sameRes(grid, fn);
-		if (vel.d.nz <= 1) errMsg(std::string(fn) + ": 2D grids are not on the B200 path");
 		if (vel.parent->dt != 1.0f) errMsg(std::string(fn) + ": only dt 1 on the B200 path");
 		CK(flof_advect_semi_lagrange_cfl3d(ctx(), cfl, vel.f(), grid.f(), grid.elem, vel.d, velFactor), fn);
 	};

@@ -320,7 +320,7 @@ int ref_optical_flow_multiscale4d(const int *d, float *vel, const float *i0,
 }
 
 /* ---- the 3D instantiations: Grid<Real> / Grid<Vec3> on a plain 3D solver ---- */
-#define SOLVER3(d) FluidSolver solver(Vec3i((d)[0], (d)[1], (d)[2]), 3, -1)
+#define SOLVER3(d) FluidSolver solver(Vec3i((d)[0], (d)[1], (d)[2]), (d)[2] > 1 ? 3 : 2, -1) /* nz == 1: a 2D solver */
 
 /* optflow4d.cpp:1175 opticalFlowMultiscale3d */
 int ref_optical_flow_multiscale3d(const int *d3, float *vel3, const float *i0, const float *i1, float wSmooth,

@@ -62,6 +62,9 @@ DIM3_CASES = {
     # the flof.py parameter set (blur, border reset, two levels, final projection) on a 3D pair
     "flof": ((32, 32, 32), dict(wSmooth=1e-3, wEnergy=1e-4, postVelBlur=4., cgAccuracy=1e-2, resetBndWidth=0.1, multiStep=3,
                                 minGridSize=20, doFinalProject=True)),
+    # a 2D grid (nz == 1): the DIM = 2 instantiation of scenes/ofblend2dTest.py, three levels, final projection
+    "plane": ((40, 36, 1), dict(wSmooth=1e-2, wEnergy=1e-4, postVelBlur=4., cgAccuracy=1e-3, resetBndWidth=0.1, multiStep=3,
+                                minGridSize=12, doFinalProject=True)),
     # projection instead of the solve on the fine level (projSizeThresh), non-cubic grid
     "proj": ((28, 24, 20), dict(wSmooth=1e-2, wEnergy=1e-4, postVelBlur=2., cgAccuracy=1e-3, resetBndWidth=0.1, multiStep=2,
                                 minGridSize=12, projSizeThresh=20)),

@@ -75,7 +75,7 @@ def test_optical_flow_multiscale3d(gpu, name):
 @pytest.mark.ref
 def test_dim3_against_the_live_reference(gpu):
     """Further inputs (odd sizes, other seeds) against the compiled reference on the box's host cores."""
-    for dims, seed in (((17, 15, 13), 1), ((22, 12, 26), 2)):
+    for dims, seed in (((17, 15, 13), 1), ((22, 12, 26), 2), ((26, 23, 1), 3)):      # the last one is a 2D grid
         sh = (dims[2], dims[1], dims[0])
         i0, i1 = sdf_pair3(dims, seed)
         vel = rnd(sh + (3,), 30 + seed, 1.5)
