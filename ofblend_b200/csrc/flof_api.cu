@@ -79,6 +79,7 @@ int flof_ctx_create(flof_ctx **out, int device)
 	c->opt.apply_zchunk = getenv("FLOF_APPLY_ZCHUNK") ? atoi(getenv("FLOF_APPLY_ZCHUNK")) : -1;
 	c->opt.dot_mode = getenv("FLOF_DOT_MODE") ? atoi(getenv("FLOF_DOT_MODE")) : 1;
 	c->opt.no_p2p = getenv("FLOF_NO_P2P") ? 1 : 0;
+	c->opt.sweep_overlap = getenv("FLOF_SWEEP_OVERLAP") ? atoi(getenv("FLOF_SWEEP_OVERLAP")) : 1;
 	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CCK(cudaDeviceGetDefaultMemPool(&c->pool, device));
 	uint64_t thr = UINT64_MAX;
@@ -103,6 +104,10 @@ int flof_ctx_destroy(flof_ctx *ctx)
 	flof_ctx_comm_destroy(ctx);
 	flof_seq_release(ctx);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
+	if (ctx->stream_hi) {
+		for (int i = 0; i < 3; ++i) cudaEventDestroy(ctx->ev_ov[i]);
+		cudaStreamDestroy(ctx->stream_hi);
+	}
 	cudaFreeHost(ctx->pinned);
 	cudaFree(ctx->cg);
 	cudaFree(ctx->red);
@@ -124,6 +129,7 @@ int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value)
 	else if (!strcmp(name, "dot_mode")) ctx->opt.dot_mode = value;
 	else if (!strcmp(name, "no_p2p")) ctx->opt.no_p2p = value;
 	else if (!strcmp(name, "apply_zchunk")) ctx->opt.apply_zchunk = value;
+	else if (!strcmp(name, "sweep_overlap")) ctx->opt.sweep_overlap = value;
 	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_set_option: unknown option '%s'", name);
 	return FLOF_OK;
 }
@@ -136,6 +142,7 @@ int flof_ctx_get_option(flof_ctx *ctx, const char *name, int *value)
 	else if (!strcmp(name, "dot_mode")) *value = ctx->opt.dot_mode;
 	else if (!strcmp(name, "no_p2p")) *value = ctx->opt.no_p2p;
 	else if (!strcmp(name, "apply_zchunk")) *value = ctx->opt.apply_zchunk;
+	else if (!strcmp(name, "sweep_overlap")) *value = ctx->opt.sweep_overlap;
 	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_get_option: unknown option '%s'", name);
 	return FLOF_OK;
 }

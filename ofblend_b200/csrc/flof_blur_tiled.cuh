@@ -369,17 +369,20 @@ static int flof_launch_expol_items(flof_ctx *ctx, const float *a, float *out, co
 // Per output the taps still arrive in the reference's order (vt, zk, yj, xi): planes ascend, rows ascend within a
 // plane, and every accumulator only ever sees the planes of its own window.
 // item = { linear id ((tl*nzb + kb)*nyb + yb)*nx + x , need-mask: bit (zo*FLOF_ETPY + oy) }
+// sel: 0 = every item of the slab; 1 = only the items of its first and last slice (their outputs are what the
+// neighbouring ranks need as ghost slices), 2 = only the others -- the two lists of the overlapped sweep (flof_blur.cu)
 template <int TZ>
 __global__ void __launch_bounds__(FLOF_BLOCK)
     k_expol_build_items_zn(const float *__restrict__ mark, uint2 *__restrict__ items, unsigned int *__restrict__ count,
-                           flof_kd d, int nyb)
+                           flof_kd d, int nyb, int sel)
 {
 	const unsigned p = blockIdx.x * FLOF_BLOCK + threadIdx.x;
 	const int kb = (int)blockIdx.y, tl = (int)blockIdx.z, t = tl + d.t0;
 	const int nzb = (d.nz + TZ - 1) / TZ;
 	unsigned mask = 0;
 	uint32_t id = 0;
-	if (p < (unsigned)(d.nx * nyb) && t >= 1 && t < d.nt - 1) {
+	const bool edge = tl == 0 || tl == (int)gridDim.z - 1;
+	if (p < (unsigned)(d.nx * nyb) && t >= 1 && t < d.nt - 1 && (sel == 0 || (sel == 1) == edge)) {
 		const int yb = (int)(p / (unsigned)d.nx), x = (int)(p - (unsigned)yb * (unsigned)d.nx);
 		if (x >= 1 && x < d.nx - 1) {
 #pragma unroll
@@ -586,7 +589,8 @@ static int64_t flof_expol_zn_capacity(const flof_ctx *ctx, flof_dim4 d, int tz)
 	const int64_t n = (int64_t)d.nx * ((d.ny + FLOF_ETPY - 1) / FLOF_ETPY) * ((d.nz + tz - 1) / tz) * (tb - ta);
 	return n < ((int64_t)1 << 31) ? n : 0;
 }
-static int flof_expol_zn_build(flof_ctx *ctx, const float *marker, flof_dim4 d, int tz, uint2 *items, unsigned int *count, int *n)
+static int flof_expol_zn_build(flof_ctx *ctx, const float *marker, flof_dim4 d, int tz, uint2 *items, unsigned int *count, int *n,
+                               int sel = 0)
 {
 	dim3 g;
 	const flof_kd kd = flof_kdim(ctx, d, &g);
@@ -595,9 +599,9 @@ static int flof_expol_zn_build(flof_ctx *ctx, const float *marker, flof_dim4 d, 
 	g.y = (unsigned)((d.nz + tz - 1) / tz);
 	FLOF_CK(cudaMemsetAsync(count, 0, sizeof(unsigned int), ctx->stream));
 	if (tz == 4)
-		FLOF_LAUNCH(k_expol_build_items_zn<4>, g, FLOF_BLOCK, 0, marker, items, count, kd, nyb);
+		FLOF_LAUNCH(k_expol_build_items_zn<4>, g, FLOF_BLOCK, 0, marker, items, count, kd, nyb, sel);
 	else
-		FLOF_LAUNCH(k_expol_build_items_zn<2>, g, FLOF_BLOCK, 0, marker, items, count, kd, nyb);
+		FLOF_LAUNCH(k_expol_build_items_zn<2>, g, FLOF_BLOCK, 0, marker, items, count, kd, nyb, sel);
 	unsigned int *h = (unsigned int *)ctx->pinned;
 	FLOF_CK(cudaMemcpyAsync(h, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
 	FLOF_CK(cudaStreamSynchronize(ctx->stream));

@@ -110,9 +110,15 @@ struct flof_ctx {
 		int apply_variant;  // CG apply: 11 (default) = streaming hints + 6 CTAs/SM (40 registers, no spills); 7 = 8 CTAs/SM; 0, 1, 3, 5, 9, 10 other occupancy / unrolling points
 		int no_p2p;         // 1: keep NCCL for halos and CG scalars (no NVLink peer mailboxes; tree-order dot products)
 		int apply_zchunk;   // CG apply: z-planes per chunk of the leaf order (-1 = by grid size, 0 = plain index order)
+		int sweep_overlap;  // sharded extrapolation sweeps: 1 (default) = boundary items + halo exchange on a high-priority
+		                    // side stream, overlapped with the interior items; 0 = exchange, then one launch
 		int dot_mode;       // CG dot products: 1 (default) = the reference's sequential summation order, bit for bit
 		                    // (flof_seqsum); 0 = tree reductions (faster, last bits of the fp64 sums differ)
 	} opt;
+	// sharded extrapolation sweeps: a high-priority side stream for the boundary items + halo exchange, so that they
+	// overlap the interior items on `stream` (flof_blur.cu); created on first use
+	cudaStream_t stream_hi;
+	cudaEvent_t ev_ov[3];
 	int64_t shard_min_cells; // smaller pyramid levels are computed replicated on every rank
 	// t-sharding of the pyramid level currently being processed (set by the multi-scale driver):
 	// every rank keeps full-size grids in a global index space but computes and owns only the
