@@ -112,6 +112,8 @@ struct flof_ctx {
 		int apply_zchunk;   // CG apply: z-planes per chunk of the leaf order (-1 = by grid size, 0 = plain index order)
 		int sweep_overlap;  // sharded extrapolation sweeps: 1 (default) = boundary items + halo exchange on a high-priority
 		                    // side stream, overlapped with the interior items; 0 = exchange, then one launch
+		int host_result_rank;  // flof_optical_flow_multiscale4d_host on N ranks: -1 (default) every rank downloads the result,
+		                       // r >= 0: only rank r does
 		int dot_mode;       // CG dot products: 1 (default) = the reference's sequential summation order, bit for bit
 		                    // (flof_seqsum); 0 = tree reductions (faster, last bits of the fp64 sums differ)
 	} opt;

@@ -428,7 +428,7 @@ extern "C" int flof_grid4d_set_bound_int(flof_ctx *ctx, int *a, flof_dim4 d, int
 }
 
 // ref: knSetBnd4dNeumann grid4d.cpp:370-407.  Source cells are never boundary cells
-// themselves (for sizes > 2w+3), so the in-place update is race-free.
+// themselves (for sizes >= 2w+3), so the in-place update is race-free.
 template <class T> __global__ void k_set_bound_neumann4d(T *a, flof_kd d, int w)
 {
 	int i, j, k, t;
@@ -448,7 +448,8 @@ template <class T> __global__ void k_set_bound_neumann4d(T *a, flof_kd d, int w)
 extern "C" int flof_grid4d_set_bound_neumann(flof_ctx *ctx, float *a, flof_dim4 d, int elem, int w)
 {
 	FLOF_ARG(elem == 1 || elem == 4, "flof_grid4d_set_bound_neumann: elem must be 1 or 4");
-	FLOF_ARG(d.nx > 2 * w + 3 && d.ny > 2 * w + 3 && d.nz > 2 * w + 3 && d.nt > 2 * w + 3,
+	// n >= 2w + 3 per axis: the source index (w+1 or n-2-w) is then no boundary index itself
+	FLOF_ARG(d.nx >= 2 * w + 3 && d.ny >= 2 * w + 3 && d.nz >= 2 * w + 3 && d.nt >= 2 * w + 3,
 	         "flof_grid4d_set_bound_neumann: grid too small for width %d", w);
 	// sharded: the source slice of a t-border cell (w+1 / nt-2-w) must lie in the same slab
 	if (flof_sharded(ctx, d.nt)) FLOF_ARG(ctx->sh.tb - ctx->sh.ta >= w + 2, "setBoundNeumann: slab thinner than the boundary width");

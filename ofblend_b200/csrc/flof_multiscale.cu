@@ -452,6 +452,9 @@ extern "C" int flof_optical_flow_multiscale4d_host(flof_ctx *ctx, float *vel_h, 
 		MS_RET(flof_memcpy_h2d(ctx, vel.p, vel_h, vb));
 	}
 	MS_RET(flof_optical_flow_multiscale4d(ctx, vel.f(), i0.f(), i1.f(), d, p, tr, err_out));
-	MS_RET(flof_memcpy_d2h(ctx, vel_h, vel.p, vb));
+	// N ranks: by default every rank receives the deformation in its host buffer; with the option host_result_rank = r
+	// only rank r downloads it (the rank that writes the .uni file) and the others skip their 16 B/cell over PCIe
+	if (ctx->opt.host_result_rank < 0 || ctx->nranks <= 1 || ctx->rank == ctx->opt.host_result_rank)
+		MS_RET(flof_memcpy_d2h(ctx, vel_h, vel.p, vb));
 	return FLOF_OK;
 }
