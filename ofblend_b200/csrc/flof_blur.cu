@@ -199,16 +199,22 @@ static int expol_sweeps_overlapped(flof_ctx *ctx, float *a, float *tmp, const fl
 		// boundary items + exchange on the side stream (after the interior items of the previous sweep)
 		if (sIt > 0) FLOF_CK(cudaStreamWaitEvent(shi, evI, 0));
 		FLOF_CK(cudaEventRecord(evI, smain));
-		ctx->stream = shi;
-		if (rc == FLOF_OK) rc = flof_launch_expol_zn(ctx, cur, oth, items, nB, d, tz, shfl);
-		cudaEventRecord(evB, shi);
-		if (rc == FLOF_OK && sIt + 1 < sweeps) rc = flof_halo_exchange(ctx, oth, d.nt, slice_bytes, 1);
-		ctx->stream = smain;
+		{
+			struct OnSide {  // the launch helpers use ctx->stream: point it at the side stream for this scope only
+				flof_ctx *c;
+				cudaStream_t back;
+				OnSide(flof_ctx *cc, cudaStream_t s) : c(cc), back(cc->stream) { c->stream = s; }
+				~OnSide() { c->stream = back; }
+			} side(ctx, shi);
+			if (rc == FLOF_OK) rc = flof_launch_expol_zn(ctx, cur, oth, items, nB, d, tz, shfl);
+			cudaEventRecord(evB, shi);
+			if (rc == FLOF_OK && sIt + 1 < sweeps) rc = flof_halo_exchange(ctx, oth, d.nt, slice_bytes, 1);
+		}
 		float *sw = cur; cur = oth; oth = sw;
 	}
 	// join: everything on the side stream, then the last interior launch is already on the main stream
-	FLOF_CK(cudaEventRecord(evB, shi));
-	FLOF_CK(cudaStreamWaitEvent(smain, evB, 0));
+	cudaEventRecord(evB, shi);
+	cudaStreamWaitEvent(smain, evB, 0);
 	if (rc == FLOF_OK && cur != a) rc = flof_memcpy_d2d(ctx, a, cur, bytes);
 	return rc;
 }
