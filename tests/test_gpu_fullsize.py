@@ -123,3 +123,45 @@ def test_gaussian_blur_is_linear_at_full_size(env):
     inner = (slice(4, -4),) * 4
     assert np.abs(out[2][inner] - (out[0][inner] + out[1][inner])).max() < 2e-5
     assert np.abs(out[3][inner] - 1.25).max() < 1e-5
+
+
+def test_mode1_at_128_matches_the_record_and_mode2_matches_the_oracle():
+    """BASELINE.json configs[4] (128^4, the north-star size) on one GPU.  A reference run of mode 1 at this size takes CPU
+    hours, so the solve itself is held to the committed single-GPU record (CG iterations of all eleven solves, final error,
+    integer checksum of the deformation's bit patterns -- the record every multi-GPU bench line is compared with), and
+    what CAN be checked against the CPU at full size is: the deformation applied to the 4D SDF (mode 2, advect4d) and the
+    error metric, both bit for bit against the oracle (pinned to the reference by tests/test_oracle_vs_ref.py)."""
+    import json
+    import os
+    from ofblend_b200 import capi, synth
+    from oracle import port
+    res = 128
+    dims = (res,) * 4
+    ctx = capi.Context(0)
+    try:
+        api = capi.HostAPI(ctx)
+        h0 = synth.post_process(synth.two_drop_phi(dims, 0), api)
+        h1 = synth.post_process(synth.two_drop_phi(dims, 1), api)
+        i0, i1 = ctx.to_device(h0), ctx.to_device(h1)
+        vel = ctx.grid(dims, 4)
+        err, tr = ctx.optical_flow_multiscale4d(vel, i0, i1, capi.make_params(**synth.MODE1_PARAMS), want_trace=True)
+        rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_n1_record.json")))["128"]
+        assert list(tr.cg_iters[:tr.n_solves]) == rec["cg_iters"]
+        assert float(err) == rec["final_error"]
+        v = vel.download()
+        u = np.ascontiguousarray(v).view(np.uint32).ravel()
+        chk = "%016x-%08x" % (int(u.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(u)))
+        assert chk == rec["deformation_checksum"], chk
+        # mode 2 at full size: GPU advect4d of the GPU deformation == oracle advect4d of the same deformation
+        g = ctx.to_device(h0)
+        ctx.advect4d(vel, g, 1.0)
+        adv = g.download().reshape(h0.shape)
+        port.set_threads(os.cpu_count() or 1)
+        want = port.advect4d(v, h0)
+        assert np.array_equal(adv, want)
+        # (fp64 sums of 2.4e8 terms in a different grouping: equal to the last float32 digit, not bit-guaranteed)
+        np.testing.assert_allclose(ctx.calc_ls_diff4d(g, i1, None, 0.005, 13), port.calc_ls_diff4d(want, h1, 0.005, 13), rtol=1e-6)
+        for x in (i0, i1, vel, g):
+            x.free()
+    finally:
+        ctx.close()
