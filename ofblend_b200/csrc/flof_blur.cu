@@ -13,7 +13,7 @@
 
 #include "flof_common.cuh"
 
-#define FLOF_BLUR_MAXS 4
+#define FLOF_BLUR_MAXS 8  // half-widths 1..4 are compile-time instantiations, 5..8 run the same kernel with a run-time width
 // weight by integer squared distance, ref gaussianWeight :128-131: exp(-dSqr/(2.*sigma*sigma))
 __constant__ float c_gauss_w[4 * FLOF_BLUR_MAXS * FLOF_BLUR_MAXS + 1];
 
@@ -36,10 +36,11 @@ __device__ __forceinline__ float4 blur_div(const float4 &v, float w)
 // one thread per interior cell (bnd 1); dst cells on the border shell are left untouched,
 // which reproduces the zero border of the fresh tmp grid after pass 1 and the original border
 // after pass 2 (ref :160-174) because the caller ping-pongs the same two buffers.
-template <class T, int S>
+template <class T, int ST>
 __global__ void __launch_bounds__(FLOF_BLOCK)
-    k_gauss_blur4d(const T *__restrict__ a, T *__restrict__ tmp, flof_kd d)
+    k_gauss_blur4d(const T *__restrict__ a, T *__restrict__ tmp, flof_kd d, int s_rt)
 {
+	const int S = ST ? ST : s_rt;  // ST == 0: run-time half-width (postVelBlur > 9)
 	int i, j, k, t;
 	if (!flof_cell_ijkt(d, i, j, k, t)) return;
 	// KERNEL(fourd, bnd = 1): a one-slice grid is not 4D in the reference (kernel.h:62-68), t is unbounded there --
@@ -82,11 +83,14 @@ static int launch_blur(flof_ctx *ctx, const T *a, T *tmp, flof_dim4 d, int s)
 	dim3 g;
 	const flof_kd kd = flof_kdim(ctx, d, &g);
 	switch (s) {
-	case 1: FLOF_LAUNCH((k_gauss_blur4d<T, 1>), g, FLOF_BLOCK, 0, a, tmp, kd); break;
-	case 2: FLOF_LAUNCH((k_gauss_blur4d<T, 2>), g, FLOF_BLOCK, 0, a, tmp, kd); break;
-	case 3: FLOF_LAUNCH((k_gauss_blur4d<T, 3>), g, FLOF_BLOCK, 0, a, tmp, kd); break;
-	case 4: FLOF_LAUNCH((k_gauss_blur4d<T, 4>), g, FLOF_BLOCK, 0, a, tmp, kd); break;
-	default: return flof_fail(ctx, FLOF_ERR_ARG, "gaussianBlur: kernel half-width %d > %d unsupported", s, FLOF_BLUR_MAXS);
+	case 1: FLOF_LAUNCH((k_gauss_blur4d<T, 1>), g, FLOF_BLOCK, 0, a, tmp, kd, s); break;
+	case 2: FLOF_LAUNCH((k_gauss_blur4d<T, 2>), g, FLOF_BLOCK, 0, a, tmp, kd, s); break;
+	case 3: FLOF_LAUNCH((k_gauss_blur4d<T, 3>), g, FLOF_BLOCK, 0, a, tmp, kd, s); break;
+	case 4: FLOF_LAUNCH((k_gauss_blur4d<T, 4>), g, FLOF_BLOCK, 0, a, tmp, kd, s); break;
+	default:
+		if (s > FLOF_BLUR_MAXS) return flof_fail(ctx, FLOF_ERR_ARG, "gaussianBlur: kernel half-width %d > %d unsupported", s, FLOF_BLUR_MAXS);
+		FLOF_LAUNCH((k_gauss_blur4d<T, 0>), g, FLOF_BLOCK, 0, a, tmp, kd, s);
+		break;
 	}
 	return FLOF_OK;
 }

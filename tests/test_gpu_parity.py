@@ -82,10 +82,14 @@ def test_bounds_minmax_ops(gpu):
     eq(gpu.grid_op4d("multConst", r, None, 1.5), port.grid_op4d("multConst", r, None, 1.5))
 
 
-@pytest.mark.parametrize("sigma", [0.5, 1.0, 1.125, 2.0])
+@pytest.mark.parametrize("sigma", [0.5, 1.0, 1.125, 2.0, 3.0, 5.0])
 def test_gaussian_blur_bitexact(gpu, sigma):
+    """half-widths 1 and 2 run the register-tiled kernels, 3 / 4 the generic one, 5 (postVelBlur 10) its run-time-width form"""
     v = rnd(SH + (4,), 9)
     eq(gpu.gaussian_blur4d(v, sigma), port.gaussian_blur4d(v, sigma))
+    if sigma >= 3.0:
+        s1 = rnd(SH, 10)
+        eq(gpu.gaussian_blur4d(s1, sigma), port.gaussian_blur4d(s1, sigma))
 
 
 def test_optical_flow4d(gpu):
