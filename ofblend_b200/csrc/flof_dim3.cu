@@ -14,7 +14,8 @@
 //    iterates of the middle slice are the reference's DIM = 3 iterates bit for bit.  Only the diagonal constant differs
 //    ((2*DIM) * wSmooth + wEnergy, ref :478-480) and is passed explicitly.
 //  * Everything else is a one-thread-per-cell 3D kernel below (3D grids are small: performance is not on the north-star
-//    path, parity is).  The multi-scale driver is the same function as in 4D (flof_multiscale.cu) with a 3D operator table.
+//    path, parity is).  The multi-scale driver is the same function as in 4D (flof_multiscale.cu): a level with nt == 1
+//    dispatches every operator to its 3D form.
 //  * 2D grids (nz == 1, the reference's DIM = 2 instantiation used by scenes/ofblend2dTest.py) take the same route: every
 //    kernel below follows the reference's `is3D()` switches, the solve embeds the plane in z and in t.
 #include <math.h>
