@@ -363,10 +363,12 @@ def roofline_of(m):
             "how": "CUDA events around every launch on the library stream, %d steps" % m["prof_steps"]}
 
 
-def cpu_baseline_sample(res, gpu_updates_per_step, api):
+def cpu_baseline_sample(res, cg_iters, cg_cells, api):
     """cpu_baseline: the reference's opticalFlow4d (assembly + Jacobi-PCG, ref optflow4d.cpp:361-553) on the finest level of
-    the benchmarked pair -- the first solve of the mode-1 run, without the blur -- timed on the host cores, then scaled to
-    the whole solve by CG cell-updates (the reference's assembly and CG are single-threaded whatever the build)."""
+    the benchmarked pair, without the blur, timed on the host cores at two CG accuracies.  The difference of the two runs
+    gives the cost of a CG iteration, the rest the cost of the assembly; both are single-threaded in the reference whatever
+    the build and scale with the cell count, so the assembly + CG share of the whole mode-1 solve follows from the product's
+    own list of solves (cells and iterations per solve; bit-identical CG: same stopping iterations as the reference)."""
     from oracle import ref
     from ofblend_b200 import synth
     if ref.available():
@@ -376,24 +378,29 @@ def cpu_baseline_sample(res, gpu_updates_per_step, api):
         kind = "port"
     cores = mod.set_threads(os.cpu_count() or 1)
     dims = (res, res, res, res)
+    cells = res ** 4
     i0 = synth.post_process(synth.two_drop_phi(dims, 0), api)   # same inputs as the GPU run (bit-identical pre-processing)
     i1 = synth.post_process(synth.two_drop_phi(dims, 1), api)
     v0 = np.zeros(i0.shape + (4,), np.float32)
-    acc = 1e-1  # a loose CG accuracy bounds the sample to ~10-20 s; the per-iteration cost does not depend on it
-    # the iteration count comes from the product's own run of the same call (bit-identical CG: same stopping iteration)
-    _, it = api.optical_flow4d(v0, i0, i1, 1e-3, 1e-4, 0., acc, 0.1, want_iters=True)
-    t0 = time.time()
-    mod.optical_flow4d(v0, i0, i1, 1e-3, 1e-4, 0., acc, 0.1)
-    sec = time.time() - t0
-    upd = max(int(it), 1) * res ** 4
-    scaled = sec * gpu_updates_per_step / upd
-    return {"value": scaled, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample_seconds": sec, "sample_cg_iterations": int(it), "cpu_cg_cell_updates_per_s": upd / sec,
-            "sample": "%s CPU implementation: opticalFlow4d(wSmooth 1e-3, wEnergy 1e-4, postVelBlur 0, cgAccuracy %.0e) on the "
-                      "%d^4 level of the benchmarked pair = assembly + %d CG iterations, %.1f s measured; scaled to the "
-                      "full solve by CG cell-updates (x%.1f; blur / projection / advection of the CPU path NOT included, "
-                      "so this under-states the CPU time -- the reference arm measures the whole solve)"
-                      % (kind, acc, res, int(it), sec, gpu_updates_per_step / upd)}
+    runs = []
+    for acc in (5e-1, 1e-1):  # loose accuracies bound the sample to ~10 s; the per-iteration cost does not depend on them
+        _, it = api.optical_flow4d(v0, i0, i1, 1e-3, 1e-4, 0., acc, 0.1, want_iters=True)   # iteration count from the product
+        t0 = time.time()
+        mod.optical_flow4d(v0, i0, i1, 1e-3, 1e-4, 0., acc, 0.1)
+        runs.append((int(it), time.time() - t0))
+    (it1, t1), (it2, t2) = runs
+    per_iter = (t2 - t1) / (it2 - it1) if it2 > it1 else t2 / max(it2, 1)
+    setup = max(t1 - it1 * per_iter, 0.)
+    est = sum(per_iter * it * c / cells + setup * c / cells for it, c in zip(cg_iters, cg_cells))
+    return {"value": est, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample_seconds": t1 + t2, "sample_cg_iterations": [it1, it2], "cpu_cg_cell_updates_per_s": cells / per_iter,
+            "cpu_seconds_per_cg_iteration": per_iter, "cpu_seconds_assembly": setup,
+            "sample": "%s CPU implementation: opticalFlow4d(wSmooth 1e-3, wEnergy 1e-4, postVelBlur 0) on the %d^4 level of the "
+                      "benchmarked pair at cgAccuracy 5e-1 / 1e-1 = assembly + %d / %d CG iterations, %.1f s + %.1f s measured "
+                      "-> %.2f s per CG iteration, %.1f s per assembly; `value` = the assembly + CG share of the whole mode-1 "
+                      "solve (%d solves, cells and iterations per solve from the timed run), blur / projection / advection of "
+                      "the CPU path NOT included -- the reference arm (--impl reference) measures the whole solve"
+                      % (kind, res, it1, it2, t1, t2, per_iter, setup, len(cg_iters))}
 
 
 def main():
@@ -498,7 +505,7 @@ def main():
                                            "deformation_checksum": mm["parity"]["deformation_checksum"]}
             json.dump(rec, open(N1_RECORD, "w"), indent=1)
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_sample(res if res <= 64 else 64, m["cg_updates_per_step"], api)
+            line["cpu_baseline"] = cpu_baseline_sample(res if res <= 64 else 64, m["cg_iters"], m["cg_cells"], api)
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     barrier_all = fdist.barrier
     barrier_all(ctx)

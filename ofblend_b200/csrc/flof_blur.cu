@@ -179,12 +179,7 @@ __global__ void __launch_bounds__(FLOF_BLOCK)
 static int expol_sweeps_overlapped(flof_ctx *ctx, float *a, float *tmp, const float *marker, flof_dim4 d, int tz, int shfl,
                                    uint2 *items, unsigned int *count, int sweeps, size_t bytes, size_t slice_bytes)
 {
-	if (!ctx->stream_hi) {
-		int lo = 0, hi = 0;
-		FLOF_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-		FLOF_CK(cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi));
-		for (int i = 0; i < 3; ++i) FLOF_CK(cudaEventCreateWithFlags(&ctx->ev_ov[i], cudaEventDisableTiming));
-	}
+	if (flof_side_stream_ensure(ctx)) return flof_fail(ctx, FLOF_ERR_CUDA, "side stream for the overlapped sweeps could not be created");
 	cudaStream_t smain = ctx->stream, shi = ctx->stream_hi;
 	cudaEvent_t evStart = ctx->ev_ov[0], evB = ctx->ev_ov[1], evI = ctx->ev_ov[2];
 	int nB = 0, nI = 0;

@@ -133,6 +133,18 @@ struct flof_ctx {
 	} sh;
 };
 
+// high-priority side stream + three untimed events for the overlapped exchanges (sweeps: flof_blur.cu, CG: flof_solve.cu)
+static inline int flof_side_stream_ensure(flof_ctx *ctx)
+{
+	if (ctx->stream_hi) return 0;
+	int lo = 0, hi = 0;
+	if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return 1;
+	if (cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi) != cudaSuccess) return 1;
+	for (int i = 0; i < 3; ++i)
+		if (cudaEventCreateWithFlags(&ctx->ev_ov[i], cudaEventDisableTiming) != cudaSuccess) return 1;
+	return 0;
+}
+
 // slab of this rank for a grid with `nt` slices: [0, nt) unless the grid belongs to the sharded level
 static inline void flof_slab(const flof_ctx *ctx, int nt, int *ta, int *tb)
 {

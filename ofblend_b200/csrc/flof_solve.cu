@@ -774,6 +774,9 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 		FLOF_LAUNCH(k_cg_init_finalize, 1, 1, 0, accuracy, ctx->cg);
 	}
 	flof_cg_state *h = (flof_cg_state *)ctx->pinned;
+	// (exchanging the ghost slices of the new search direction on the side stream while k_cg_direction still updates the
+	// interior slices was measured at 2 GPUs: bit-identical, no gain -- the push contends with the direction kernel for
+	// the same HBM bandwidth: 178.8 vs 176.7-178.9 ms at 64^4 -- and is not kept)
 	int launched = 0;
 	// poll the device-side done flag every `chunk` iterations; iterations after convergence are
 	// no-op kernels (early return on st->done)
