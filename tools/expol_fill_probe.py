@@ -29,6 +29,9 @@ def main():
     del m
     need = int(un.sum())
     print("res %d cells %d needed %d (%.4f)" % (res, un.size, need, need / un.size))
+    for P in (2, 4, 8):  # how evenly the sweep work spreads over the t-slabs of P ranks
+        per = un.reshape(P, res // P, -1).sum(axis=(1, 2)).astype(np.float64)
+        print("P=%d: needed cells per t-slab / mean: %s  (max %.3f)" % (P, " ".join("%.2f" % x for x in per / per.mean()), per.max() / per.mean()))
     shell = un.copy()
     shell[2:-2, 2:-2, 2:-2, 2:-2] = False
     print("needed cells on the index-1 shell: %.4f of needed" % (shell.sum() / need))
