@@ -474,6 +474,21 @@ def main():
         finally:
             ctx.set_option("dot_mode", 1)
 
+    if res == 64 and not args.no_tree_record:
+        # the same solve with the opt-in separable Gaussian blur (blur_mode 1; exact dot products kept): what the bit-exact
+        # (2S+1)^4-tap blur costs, and how far the result moves without it
+        try:
+            ctx.set_option("blur_mode", 1)
+            ms = measure(ctx, api, fdist, res, 3, 1, world, local_rank, False, 1, check_n1=False)
+            config["separable_blur_mode"] = {"note": "blur_mode 1 (NOT the default): Gaussian blur as four 1D fp32 passes instead of the "
+                                                     "reference's (2S+1)^4-tap sums; everything else as in `value`",
+                                             "value": ms["ms_per_step"] / 1e3, "unit": UNIT, "steps": 3, "warmup": 1,
+                                             "cg_iters": ms["cg_iters"], "vs_reference_run": ms["parity"].get("vs_reference_run")}
+        except Exception as e:  # noqa: BLE001
+            config["separable_blur_mode"] = {"error": str(e)[:300]}
+        finally:
+            ctx.set_option("blur_mode", 0)
+
     line = {"metric": METRIC, "value": m["ms_per_step"] / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -81,6 +81,7 @@ int flof_ctx_create(flof_ctx **out, int device)
 	c->opt.no_p2p = getenv("FLOF_NO_P2P") ? 1 : 0;
 	c->opt.sweep_overlap = getenv("FLOF_SWEEP_OVERLAP") ? atoi(getenv("FLOF_SWEEP_OVERLAP")) : 1;
 	c->opt.host_result_rank = -1;
+	c->opt.blur_mode = getenv("FLOF_BLUR_MODE") ? atoi(getenv("FLOF_BLUR_MODE")) : 0;
 	CCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CCK(cudaDeviceGetDefaultMemPool(&c->pool, device));
 	uint64_t thr = UINT64_MAX;
@@ -132,6 +133,7 @@ int flof_ctx_set_option(flof_ctx *ctx, const char *name, int value)
 	else if (!strcmp(name, "apply_zchunk")) ctx->opt.apply_zchunk = value;
 	else if (!strcmp(name, "sweep_overlap")) ctx->opt.sweep_overlap = value;
 	else if (!strcmp(name, "host_result_rank")) ctx->opt.host_result_rank = value;
+	else if (!strcmp(name, "blur_mode")) ctx->opt.blur_mode = value;
 	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_set_option: unknown option '%s'", name);
 	return FLOF_OK;
 }
@@ -146,6 +148,7 @@ int flof_ctx_get_option(flof_ctx *ctx, const char *name, int *value)
 	else if (!strcmp(name, "apply_zchunk")) *value = ctx->opt.apply_zchunk;
 	else if (!strcmp(name, "sweep_overlap")) *value = ctx->opt.sweep_overlap;
 	else if (!strcmp(name, "host_result_rank")) *value = ctx->opt.host_result_rank;
+	else if (!strcmp(name, "blur_mode")) *value = ctx->opt.blur_mode;
 	else return flof_fail(ctx, FLOF_ERR_ARG, "flof_ctx_get_option: unknown option '%s'", name);
 	return FLOF_OK;
 }

@@ -114,6 +114,8 @@ struct flof_ctx {
 		                    // side stream, overlapped with the interior items; 0 = exchange, then one launch
 		int host_result_rank;  // flof_optical_flow_multiscale4d_host on N ranks: -1 (default) every rank downloads the result,
 		                       // r >= 0: only rank r does
+		int blur_mode;      // Gaussian blur: 0 (default) = the reference's (2S+1)^4-tap sums, bit for bit; 1 = separable fp32
+		                    // passes (opt-in, ~6e-6 rel-L2 per blur: measures what exactness costs)
 		int dot_mode;       // CG dot products: 1 (default) = the reference's sequential summation order, bit for bit
 		                    // (flof_seqsum); 0 = tree reductions (faster, last bits of the fp64 sums differ)
 	} opt;

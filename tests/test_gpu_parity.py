@@ -92,6 +92,25 @@ def test_gaussian_blur_bitexact(gpu, sigma):
         eq(gpu.gaussian_blur4d(s1, sigma), port.gaussian_blur4d(s1, sigma))
 
 
+def test_separable_blur_option_is_close_but_not_the_default(gpu):
+    """blur_mode 1 (opt-in): four 1D passes.  Same clipping / normalisation, fp32 rounding differs: ~1e-6 relative."""
+    assert gpu.ctx.get_option("blur_mode") == 0
+    v = rnd(SH + (4,), 9)
+    s1 = rnd(SH, 10)
+    try:
+        gpu.ctx.set_option("blur_mode", 1)
+        for sigma in (1.0, 2.0, 3.0):
+            for x in (v, s1):
+                got, want = gpu.gaussian_blur4d(x, sigma), port.gaussian_blur4d(x, sigma)
+                assert rel_l2(got, want) < 2e-6
+                assert not np.array_equal(got, want) or sigma == 1.0
+                shell = np.ones(SH, bool)
+                shell[1:-1, 1:-1, 1:-1, 1:-1] = False
+                assert np.array_equal(got[shell], want[shell])      # the border shell is handled like the exact path
+    finally:
+        gpu.ctx.set_option("blur_mode", 0)
+
+
 def test_optical_flow4d(gpu):
     i0, i1 = sdf_pair(D)
     v0 = np.zeros(SH + (4,), np.float32)
