@@ -140,7 +140,9 @@ class Context:
         self._chk(self.lib.flof_sync(self.h))
 
     def set_option(self, name, value):
-        """Kernel selection knob (all choices bit-identical): expol_mode, expol_variant, apply_variant."""
+        """Context option (flof_ctx_set_option).  Kernel choices that are bit-identical: expol_mode, expol_variant, apply_variant,
+        apply_zchunk, sweep_overlap; multi-GPU plumbing: no_p2p, host_result_rank; opt-in arithmetic changes (NOT the reference's
+        bits): dot_mode 0 (tree-reduced CG dot products), blur_mode 1 (separable Gaussian)."""
         self._chk(self.lib.flof_ctx_set_option(self.h, name.encode(), int(value)))
 
     def get_option(self, name):
