@@ -1,6 +1,9 @@
 """Pretty-prints a bench.py JSON line: python tools/show_bench.py gpurun_out/bench.json"""
 import json
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` closes the pipe early: exit quietly
 
 d = json.load(open(sys.argv[1]))
 print("ms_per_step %.2f  e2e %.4f s  iters %s  final_err %s  launches %s" % (
