@@ -133,6 +133,19 @@ void orc_load_advect_time_slice_unopt(const float *defo, orc_dim4 dd, float *dst
                                       float loadTimeScale, const float defoOffset[4], const float defoScale[4],
                                       const float defoFactor[4], const float overrideSize[4], float overrideTimeOff,
                                       float defoAniFac, int zeroVel);
+/* ---- oracle/flof_oracle3.c: the 3D / 2D instantiations; grids nx*ny*nz, velocities 3 floats per cell ---- */
+/* optflow4d.cpp:863-872 advectSemiLagrangeCfl (elem 1: Grid<Real>, 3: Grid<Vec3> payload) */
+void orc3_advect_cfl(float cfl, const float *vel3, float *grid, int elem, int nx, int ny, int nz, float velFactor);
+/* optflow4d.cpp:928-933 calcLsDiff3d */
+float orc3_calc_ls_diff(const float *i0, const float *i1, float *out, int nx, int ny, int nz, float correction, int bnd);
+/* optflow4d.cpp:803-812 corrVelsOf3d */
+void orc3_corr_vels(float *dst3, float *vel3, const float *phiOrg, const float *phiTarget, int nx, int ny, int nz,
+                    float threshPhi, float postVelBlur, float resetBndWidth, int maxIter);
+/* optflow4d.cpp:1175-1188 opticalFlowMultiscale3d; cgIters / errs (optional, >= 64 entries) receive the trace */
+float orc3_optical_flow_multiscale(float *vel3, const float *i0, const float *i1, int nx, int ny, int nz, float wSmooth,
+                                   float wEnergy, float postVelBlur, float cgAccuracy, float cfl, float resetBndWidth,
+                                   int multiStep, int projSizeThresh, int minGridSize, int doFinalProject, int *cgIters,
+                                   int *nIters, float *errs, int *nErrs);
 #ifdef __cplusplus
 }
 #endif

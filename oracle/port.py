@@ -187,6 +187,58 @@ def optical_flow_multiscale4d(vel, i0, i1, wSmooth=0., wEnergy=0., postVelBlur=0
     return v
 
 
+# ---- 3D / 2D instantiations (oracle/flof_oracle3.c): numpy layout [z, y, x(, 3)]
+def _n3(a):
+    return int(a.shape[2]), int(a.shape[1]), int(a.shape[0])
+
+
+def advect_semi_lagrange_cfl3d(cfl, vel, grid, velFactor=1.):
+    v = _f32(vel)
+    g = _f32(grid).copy()
+    lib().orc3_advect_cfl(C.c_float(cfl), _p(v), _p(g), 3 if g.ndim == 4 else 1, *_n3(v), C.c_float(velFactor))
+    return g
+
+
+def calc_ls_diff3d(i0, i1, correction=1., bnd=0, want_out=False):
+    a = _f32(i0)
+    b = _f32(i1)
+    out = np.zeros(a.shape, np.float32) if want_out else None
+    fn = lib().orc3_calc_ls_diff
+    fn.restype = C.c_float
+    r = fn(_p(a), _p(b), _p(out), *_n3(a), C.c_float(correction), int(bnd))
+    return (r, out) if want_out else r
+
+
+def corr_vels_of3d(dst, vel, phiOrg, phiTarget, threshPhi=1e10, postVelBlur=0., resetBndWidth=-1., maxIter=100):
+    d = _f32(dst).copy()
+    v = _f32(vel).copy()
+    po = _f32(phiOrg)
+    pt = _f32(phiTarget)
+    lib().orc3_corr_vels(_p(d), _p(v), _p(po), _p(pt), *_n3(po), C.c_float(threshPhi), C.c_float(postVelBlur),
+                         C.c_float(resetBndWidth), int(maxIter))
+    return d, v
+
+
+def optical_flow_multiscale3d(vel, i0, i1, wSmooth=0., wEnergy=0., postVelBlur=0., cgAccuracy=1e-4, cfl=999.,
+                              resetBndWidth=-1., multiStep=1, projSizeThresh=9999, minGridSize=10, doFinalProject=False,
+                              want_trace=False):
+    v = _f32(vel).copy()
+    i0 = _f32(i0)
+    i1 = _f32(i1)
+    iters = (C.c_int * 64)()
+    errs = (C.c_float * 64)()
+    ni = C.c_int(0)
+    ne = C.c_int(0)
+    fn = lib().orc3_optical_flow_multiscale
+    fn.restype = C.c_float
+    fn(_p(v), _p(i0), _p(i1), *_n3(i0), C.c_float(wSmooth), C.c_float(wEnergy), C.c_float(postVelBlur),
+       C.c_float(cgAccuracy), C.c_float(cfl), C.c_float(resetBndWidth), int(multiStep), int(projSizeThresh),
+       int(minGridSize), int(bool(doFinalProject)), iters, C.byref(ni), errs, C.byref(ne))
+    if want_trace:
+        return v, list(iters[:ni.value]), [float(x) for x in errs[:ne.value]]
+    return v
+
+
 def extrap4d_ls_simple(phi, distance=4, inside=False, want_marker=False):
     p = _f32(phi).copy()
     mk = np.zeros(p.shape, np.int32) if want_marker else None

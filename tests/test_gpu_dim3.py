@@ -1,7 +1,7 @@
 """Parity of the 3D instantiations (opticalFlowMultiscale3d, corrVelsOf3d, advectSemiLagrangeCfl,
-calcLsDiff3d) through the C ABI.  There is no plain-C restatement of these four: the checker is the reference itself --
-its outputs committed as tests/golden/dim3_ops.npz (tests/golden/make_golden3d.py), and, where oracle/_ref/libofref.so
-travelled to the box, the compiled reference run live on further inputs.  Bar: bit-exact (all fp32 arithmetic follows the
+calcLsDiff3d) through the C ABI.  Checkers: the reference's outputs committed as tests/golden/dim3_ops.npz
+(tests/golden/make_golden3d.py), the plain-C restatement oracle/flof_oracle3.c on further inputs, and, where
+oracle/_ref/libofref.so travelled to the box, the compiled reference run live.  Bar: bit-exact (all fp32 arithmetic follows the
 reference's order; the CG runs through the 4D kernels with the reference's sequential-order dot products)."""
 import os
 
@@ -89,3 +89,27 @@ def test_dim3_against_the_live_reference(gpu):
                  doFinalProject=True)
         v0 = np.zeros(sh + (3,), np.float32)
         eq(gpu.optical_flow_multiscale3d(v0, i0, i1, **p), ref.optical_flow_multiscale3d(v0, i0, i1, **p))
+
+
+def test_dim3_against_the_c_restatement(gpu):
+    """Further inputs against oracle/flof_oracle3.c (pinned bit for bit to the reference by tests/test_dim3_golden.py);
+    needs no compiled reference on the box."""
+    from oracle import port
+    for dims, seed in (((19, 14, 12), 5), ((24, 21, 1), 6)):
+        sh = (dims[2], dims[1], dims[0])
+        i0, i1 = sdf_pair3(dims, seed)
+        vel = rnd(sh + (3,), 40 + seed, 1.5)
+        eq(gpu.advect_semi_lagrange_cfl3d(0.7, vel, i1), port.advect_semi_lagrange_cfl3d(0.7, vel, i1))
+        eq(gpu.advect_semi_lagrange_cfl3d(999., vel, vel, 0.5), port.advect_semi_lagrange_cfl3d(999., vel, vel, 0.5))
+        assert np.float32(gpu.calc_ls_diff3d(i0, i1, 1.0, 1)) == np.float32(port.calc_ls_diff3d(i0, i1, 1.0, 1))
+        z = np.zeros(sh + (3,), np.float32)
+        gd, gv = gpu.corr_vels_of3d(z, vel * np.float32(0.3), i0, i1, 4., 4., 0.1, 40)
+        pd, pv = port.corr_vels_of3d(z, vel * np.float32(0.3), i0, i1, 4., 4., 0.1, 40)
+        eq(gd, pd)
+        eq(gv, pv)
+        p = dict(wSmooth=5e-3, wEnergy=1e-4, postVelBlur=2., cgAccuracy=1e-3, resetBndWidth=0.1, multiStep=3, minGridSize=10,
+                 doFinalProject=True)
+        a, it_a, err_a = gpu.optical_flow_multiscale3d(z, i0, i1, want_trace=True, **p)
+        b, it_b, err_b = port.optical_flow_multiscale3d(z, i0, i1, want_trace=True, **p)
+        assert it_a == it_b
+        eq(a, b)
