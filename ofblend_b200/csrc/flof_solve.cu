@@ -783,7 +783,12 @@ static int cg_run(flof_ctx *ctx, float *x, float *res, float *srch, float *tmp, 
 	int chunk = 8;
 	while (true) {
 		FLOF_CK(cudaMemcpyAsync(h, ctx->cg, sizeof(flof_cg_state), cudaMemcpyDeviceToHost, ctx->stream));
+		unsigned int *perr = (unsigned int *)((char *)ctx->pinned + 2048);
+		*perr = 0;
+		if (multi == 2) FLOF_CK(cudaMemcpyAsync(perr, ctx->p2p.dev.err, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
 		FLOF_CK(cudaStreamSynchronize(ctx->stream));
+		// a peer-mailbox wait that timed out leaves stale ghost slices / scalars: stop here instead of iterating on them
+		if (*perr) return flof_fail(ctx, FLOF_ERR_CUDA, "opticalFlow4d: peer mailbox wait timed out during the CG (ranks out of step?)");
 		if (h->done || launched >= maxIter) break;
 		for (int q = 0; q < chunk && launched < maxIter; ++q, ++launched) {
 			if (multi) FLOF_RET(flof_halo_exchange(ctx, srch, d.nt, slice_bytes, 1));
